@@ -1,0 +1,217 @@
+/* moco_flow_b200 -- C ABI of the B200-native MoCo-Flow ray-rendering hot path.
+ *
+ * One shared library (moco_flow_b200/csrc/libmoco_flow_b200.so), plain pointers and sizes, no C++
+ * or torch types.  All pointers are DEVICE pointers unless the name ends in `_host`.  Every entry
+ * is stream-ordered, allocates nothing, never synchronises, and returns 0 on success, a positive
+ * cudaError_t, or a negative MCF_ERR_* code.
+ *
+ * The reference (wyysf-98/MoCo_Flow) has no FFI: its boundary for this path is a set of Python
+ * callables.  Each entry below names the reference code it replaces (paths relative to the
+ * reference root); `moco_flow_b200/*.py` re-creates the Python callables on top of these entries
+ * and INTEGRATION.md shows the import switch a maintainer makes.
+ */
+#ifndef MOCO_FLOW_B200_H_
+#define MOCO_FLOW_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define MCF_ABI_VERSION 1
+#define MCF_MAX_FREQS 24
+#define MCF_TILE_ROWS 128      /* samples per tensor-core tile                      */
+#define MCF_BLOCK_BYTES 16384  /* one [128 rows][64 bf16] 128B-swizzled image block */
+
+#define MCF_ACT_RELU 0
+#define MCF_ACT_SOFTPLUS 1
+
+#define MCF_ERR_BAD_ARG (-1)
+#define MCF_ERR_UNSUPPORTED (-2)
+#define MCF_ERR_DEVICE_FLAG (-3)
+
+int mcf_abi_version(void);
+/* Reads (and clears) the device-side protocol error flag set by a kernel whose bounded barrier
+ * wait expired.  Synchronises the device; for tests and debugging only. */
+int mcf_device_error_flag(unsigned int* flag_host);
+
+/* ---- sampling ------------------------------------------------------------------------------ */
+/* models/rendering.py:245-263  z_vals (+stratified jitter) and xyz = o + d*z.
+ * rays: [n_rays][ray_stride] rows [o(3) d(3) near far ...]; t_steps = linspace(0,1,n_samples). */
+int mcf_coarse_samples(const float* rays, int ray_stride, const float* t_steps, const float* perturb_rand,
+                       float perturb, int use_disp, int n_rays, int n_samples, float* z_out, float* xyz_out,
+                       cudaStream_t stream);
+/* models/rendering.py:329-330 */
+int mcf_ray_points(const float* rays, int ray_stride, const float* z, int n_rays, int n_samples, float* xyz_out,
+                   cudaStream_t stream);
+
+/* ---- positional encoding (standalone Embedding.forward), models/embedding.py:42-46 ---------- */
+int mcf_pe_fwd(const float* x, long long n_rows, int in_channels, int n_freqs, const float* freqs_host,
+               const float* weights_host, float* out, int out_stride, cudaStream_t stream);
+int mcf_pe_bwd(const float* x, const float* dy, long long n_rows, int in_channels, int n_freqs,
+               const float* freqs_host, const float* weights_host, int dy_stride, float* dx, cudaStream_t stream);
+
+/* out[r][n] = bias[n] + sum_j W[n][col_off+j] * feat[r][j]: exact fp32 fold of the per-ray constant
+ * input columns (replaces the repeat_interleave+cat of models/rendering.py:73-75,133-142). */
+int mcf_ray_bias(const float* W, int w_stride, int col_off, const float* bias, const float* feat, int feat_stride,
+                 int n_feat, int n_rays, int n_out, float* out, cudaStream_t stream);
+
+/* ---- alpha compositing, models/rendering.py:158-190 ---------------------------------------- */
+/* sigma at sigma[m*sigma_stride]; rgb (may be NULL: weights-only) at rgb[m*rgb_stride+0..2]. */
+int mcf_composite_fwd(const float* sigma, int sigma_stride, const float* rgb, int rgb_stride, const float* z,
+                      const float* dirs, int dir_stride, const float* noise, float noise_std, const float* background,
+                      int activation, int n_rays, int n_samples, float* weights, float* alphas, float* rgb_out,
+                      float* depth_out, float* opacity_out, cudaStream_t stream);
+/* analytic backward of the above w.r.t. sigma and rgb (what autograd derives for :158-190) */
+int mcf_composite_bwd(const float* sigma, int sigma_stride, const float* rgb, int rgb_stride, const float* z,
+                      const float* dirs, int dir_stride, const float* noise, float noise_std, const float* background,
+                      int activation, int n_rays, int n_samples, const float* g_rgb, const float* g_depth,
+                      const float* g_opacity, const float* g_weights, float* d_sigma, int d_sigma_stride, float* d_rgb,
+                      int d_rgb_stride, cudaStream_t stream);
+
+/* ---- sample_pdf, models/rendering.py:5-46 (+ the sort-merge of :326) ------------------------ */
+/* bins: [n_rays][n_bins+1] (or, with bins_are_z, the coarse depths whose mid-points are the bins);
+ * weights: [n_rays][n_bins] (ignored when cdf_in is given: "level 1" entry that consumes a
+ * caller-built cdf [n_rays][n_bins+1]); u: [n_rays][n_importance].  Optional outputs: samples,
+ * inds_out (searchsorted result), cdf_out, z_merged = sort(cat(z_coarse, samples)). */
+int mcf_sample_pdf(const float* bins, int bins_stride, int bins_are_z, const float* weights, int w_stride,
+                   const float* cdf_in, int cdf_stride, const float* u, int u_stride, float eps, int n_rays, int n_bins,
+                   int n_importance, const float* z_coarse, int zc_stride, int n_coarse, float* samples, int* inds_out,
+                   float* cdf_out, float* z_merged, cudaStream_t stream);
+
+/* ---- flow-consistency residual, models/rendering.py:304-314,363-373 ------------------------- */
+/* resid[m] = mean_3 |a-b| ; stats = {masked sum, masked count, total sum} (3 doubles);
+ * mean_out[0] = mean of resid over alphas>=thresh (over everything if the mask is empty). */
+int mcf_masked_l1_fwd(const float* a, const float* b, const float* alphas, float thresh, long long n_points,
+                      float* resid, double* stats, float* mean_out, cudaStream_t stream);
+int mcf_masked_l1_bwd(const float* a, const float* b, const float* alphas, float thresh, long long n_points,
+                      const float* g_resid, const float* g_mean, const double* stats, float* d_b, cudaStream_t stream);
+
+/* ---- fused MLP chains on tcgen05/TMEM: models/nerf.py:61-102, models/nof.py:55-85 ----------- */
+/* Weights are re-packed from the fp32 nn.Linear tensors into bf16 128B-swizzled UMMA operand images
+ * (and fp32 constants) by mcf_pack; a chain launch then streams those images with bulk copies.
+ * The tables are built by the host shim (moco_flow_b200/plans.py) and are opaque to callers. */
+typedef struct {
+  uint32_t dst_off;   /* byte offset into the packed stream (kind 0) / float offset into consts (kind 1) */
+  uint32_t bytes;     /* kind 0: image bytes = padded_rows*128 ; kind 1: number of floats                 */
+  int32_t kind;       /* 0: bf16 swizzled image block, 1: fp32 copy                                       */
+  int32_t tensor;     /* index into the pointer array                                                     */
+  int32_t row0, nrows;
+  int32_t col0, ncols;
+  int32_t ld;         /* source leading dimension (elements)                                              */
+  int32_t transposed; /* image(r,c) = src[(col0+c)*ld + row0+r] instead of src[(row0+r)*ld + col0+c]      */
+} mcf_pack_t;
+
+#define MCF_MAX_PACK_TENSORS 32
+int mcf_pack(const mcf_pack_t* table_dev, int n_entries, const float* const* tensors_host, int n_tensors,
+             void* wpack, float* consts, cudaStream_t stream);
+
+typedef struct {
+  uint32_t src_off; /* byte offset of the chunk image in the packed stream */
+  uint32_t bytes;
+  uint8_t a_buf;    /* 0: input block X0, 1: activation buffer H */
+  uint8_t a_kblock; /* 64-column block of that buffer            */
+  uint8_t ksteps;   /* K=16 MMAs issued from this chunk (1..4)   */
+  uint8_t flags;    /* bit0: first MMA overwrites the accumulator */
+  uint16_t n;       /* MMA N                                       */
+  uint16_t acc_col; /* accumulator column offset inside the slot   */
+} mcf_chunk_t;
+
+typedef struct {
+  uint16_t epi;      /* MCF_EPI_*                                                   */
+  uint16_t n_out;    /* accumulator columns this epilogue consumes                  */
+  uint16_t acc_col;  /* first accumulator column                                    */
+  uint16_t chunk_begin, chunk_end;
+  int16_t raybias;   /* -1, or index of the per-ray bias matrix [n_rays][n_out]     */
+  uint32_t const_off;/* float offset of the column bias in consts                   */
+  uint32_t aux_off;  /* float offset of head weights (sigma / rgb) in consts        */
+  uint32_t save_off; /* byte offset inside the per-tile save record, 0xFFFFFFFF none */
+  uint32_t mask_off; /* word offset inside the per-tile mask record, 0xFFFFFFFF none */
+  uint32_t reserved;
+} mcf_round_t;
+
+#define MCF_EPI_RELU 0         /* H = relu(acc + bias)                                  */
+#define MCF_EPI_RELU_SIGMA 1   /* + sigma = h . w_sigma + b_sigma                       */
+#define MCF_EPI_LINEAR 2       /* H = acc + bias                                        */
+#define MCF_EPI_NERF_RGB 3     /* he = relu(acc+bias); rgb = sigmoid(W_rgb he + b_rgb)  */
+#define MCF_EPI_NOF_HEAD 4     /* quaternion / residual head of NoF                     */
+#define MCF_EPI_B_MASK 16      /* H = acc * mask                                        */
+#define MCF_EPI_B_MASK_SIGMA 17/* H = (acc + d_sigma w_sigma) * mask                    */
+#define MCF_EPI_B_LINEAR 18    /* H = acc                                               */
+#define MCF_EPI_B_DPE 19       /* d_xyz += J_PE^T acc                                   */
+
+#define MCF_PRO_PE_XYZ 0  /* X0 = PE(xyz[m]) zero-padded                      */
+#define MCF_PRO_DENSE 1   /* X0 = dense[m, :dense_cols] zero-padded           */
+#define MCF_PRO_B_NERF 2  /* backward of the NeRF heads                       */
+#define MCF_PRO_B_NOF 3   /* backward of the NoF head                         */
+
+typedef struct {
+  /* program */
+  const mcf_chunk_t* chunks;
+  const mcf_round_t* rounds;
+  int32_t n_chunks, n_rounds;
+  int32_t width;    /* hidden width: 128 or 256 */
+  int32_t prologue; /* MCF_PRO_*                */
+  const void* wpack;
+  const float* consts;
+  const float* raybias[4];
+  /* problem */
+  long long n_rows;        /* M = rays*samples (or points)                   */
+  int32_t rows_per_ray;    /* S: ray(m) = m / S                              */
+  int32_t n_rays;
+  /* prologue inputs */
+  const float* xyz;        /* [M][3]                                         */
+  const float* dense;      /* [M][dense_stride] (MCF_PRO_DENSE)              */
+  int32_t dense_stride, dense_cols;
+  int32_t pe_n_freqs, pe_pad_to;
+  float pe_freq[MCF_MAX_FREQS];
+  float pe_weight[MCF_MAX_FREQS];
+  /* outputs */
+  float* out;              /* NeRF: [M][out_stride] (rgb at +0..2, sigma at +sigma_col); NoF: [M][3] */
+  int32_t out_stride, sigma_col;
+  int32_t use_quat;
+  float* head_save;        /* NoF: [M][12] fp32 {v,s,t,x} for the backward, or NULL */
+  /* training saves (NULL = inference) */
+  void* save;              /* per-tile records of bf16 images                */
+  long long save_tile_bytes;
+  uint32_t* masks;         /* per-tile ReLU bit masks                        */
+  long long mask_tile_words;
+  uint32_t x0_save_off;    /* 0xFFFFFFFF none                                */
+  /* backward inputs */
+  const float* g_out;      /* NeRF: [M][4] grad of rgbsigma; NoF: [M][3] grad of xyz_out */
+  const float* fwd_out;    /* NeRF: forward [M][4] output                    */
+  const void* fwd_save;    /* forward save records                           */
+  long long fwd_save_tile_bytes;
+  const uint32_t* fwd_masks;
+  long long fwd_mask_tile_words;
+  uint32_t fwd_x0_off, fwd_he_off;
+  float* d_xyz;            /* [M][3] grad w.r.t. the input points, or NULL   */
+  float* d_head;           /* NeRF: [M][4] {d_pre_rgb(3), d_sigma}; NoF: unused */
+  int32_t max_ctas;        /* 0 = one CTA per SM                             */
+} mcf_chain_params_t;
+
+int mcf_chain_launch(const mcf_chain_params_t* params_host, cudaStream_t stream);
+
+/* dW[i][j] (+)= sum_rows P[row][i] * Q[row][j] over bf16 tile images (split-K over row tiles, fp32
+ * atomics into a zero-initialised or accumulating output): the weight-gradient GEMM of the MLP
+ * backward.  P/Q tile records: image(tile) at base + tile*tile_bytes + off; blocks of 64 columns.
+ * out[i*ld_out + j]; i < n_i (<= 256), j < n_j (<= 256). */
+typedef struct {
+  const void* p_base; long long p_tile_bytes; uint32_t p_off; int32_t p_cols;
+  const void* q_base; long long q_tile_bytes; uint32_t q_off; int32_t q_cols;
+  float* out; int32_t ld_out; int32_t n_i, n_j;
+  float* colsum_p;   /* optional: colsum_p[i] += sum_rows P[row][i] (bias gradient) */
+  long long n_tiles;
+  int32_t max_ctas;
+} mcf_dw_params_t;
+int mcf_dw_gemm(const mcf_dw_params_t* params_host, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOCO_FLOW_B200_H_ */

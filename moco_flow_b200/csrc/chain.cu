@@ -1,0 +1,699 @@
+// Fused MLP chains on tcgen05 / TMEM (sm_100a only).
+//
+// One persistent CTA per SM works on two 128-sample tiles ("slots") at a time.  Warp roles:
+//   warp 0      : weight producer -- streams pre-swizzled bf16 weight chunk images (16 KB each) from
+//                 L2/HBM into a 4-stage shared-memory ring with 1-D bulk async copies (UBLKCP)
+//   warp 1      : MMA issuer -- one thread issues tcgen05.mma (M=128, N<=128 per chunk, K=16 steps);
+//                 accumulators live in TMEM (256 columns per slot)
+//   warp 2      : TMEM allocator
+//   warps 4-7   : epilogue group of slot 0, warps 8-11: epilogue group of slot 1 (thread == tile row):
+//                 build the first-layer operand (positional encoding fused here), then per layer
+//                 TMEM -> registers -> bias/activation -> bf16 -> 128B-swizzled smem operand of the
+//                 next layer, so activations never leave the SM.  The two slots ping-pong: while the
+//                 tensor core runs layer l of slot B, slot A's epilogue of layer l is in flight.
+// The layer program (which chunks feed which accumulator columns, which epilogue follows) is a table
+// built by the host shim, so the same kernel runs NeRF / NoF forward and their backward dX chains.
+//
+// Reference semantics: models/nerf.py:61-102, models/nof.py:55-85, models/embedding.py:42-46.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/moco_flow_b200.h"
+#include "ptx.cuh"
+
+namespace mcf {
+
+constexpr int kThreads = 384;
+constexpr int kStages = 4;
+constexpr uint32_t kBlk = MCF_BLOCK_BYTES;
+constexpr int kMaxChunks = 128;
+constexpr int kMaxRounds = 24;
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr uint32_t kSlotCols = 256;
+
+struct Tables {
+  mcf_chunk_t chunks[kMaxChunks];  // 2048 B
+  mcf_round_t rounds[kMaxRounds];  // 768 B
+  uint64_t w_full[kStages];
+  uint64_t w_empty[kStages];
+  uint64_t act_ready[2];
+  uint64_t acc_full[2];
+  uint32_t tmem_base;
+  uint32_t pad[3];
+};
+
+template <int W>
+struct Smem {
+  static constexpr uint32_t kHBlocks = W / 64;
+  static constexpr uint32_t kHBytes = kHBlocks * kBlk;
+  static constexpr uint32_t off_h = 0;
+  static constexpr uint32_t off_x0 = off_h + 2 * kHBytes;
+  static constexpr uint32_t off_ring = off_x0 + 2 * kBlk;
+  static constexpr uint32_t off_tab = off_ring + kStages * kBlk;
+  static constexpr uint32_t total = off_tab + sizeof(Tables);
+};
+static_assert(Smem<256>::total <= 232448, "shared memory budget exceeded");
+
+// ---------------------------------------------------------------------------------------------
+// epilogue helpers (thread == row)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_h8(uint8_t* hbuf, uint32_t row, uint32_t col0, uint4 v) {
+  uint32_t block = col0 >> 6, c16 = (col0 & 63u) >> 3;
+  *reinterpret_cast<uint4*>(hbuf + block * kBlk + sw128_off(row, c16)) = v;
+}
+
+// pack 32 fp32 -> 32 bf16 and store as 4 x 16 B into the swizzled activation buffer
+__device__ __forceinline__ void store_h32(uint8_t* hbuf, uint32_t row, uint32_t col0, const float (&f)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 v;
+    v.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+    v.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+    v.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+    v.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+    store_h8(hbuf, row, col0 + q * 8, v);
+  }
+}
+
+__device__ __forceinline__ void load32f(const float* __restrict__ p, float (&b)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
+    b[q * 4 + 0] = t.x;
+    b[q * 4 + 1] = t.y;
+    b[q * 4 + 2] = t.z;
+    b[q * 4 + 3] = t.w;
+  }
+}
+
+struct RowState {   // per-thread state that lives across the rounds of one tile
+  float sigma;      // fwd: sigma head value; bwd: d_sigma
+  float dx[3];      // bwd: accumulated d_xyz
+  float aux[4];
+};
+
+// quaternion head of NoF (models/nof.py:75-80 with kornia 0.6.5 semantics)
+__device__ __forceinline__ void nof_quat_apply(const float* h9, const float* x, float* out) {
+  float v0 = h9[0], v1 = h9[1], v2 = h9[2];
+  float n = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-8f);
+  float sn, cs;
+  sincosf(n, &sn, &cs);
+  float a = sn / n;
+  float q0 = v0 * a, q1 = v1 * a, q2 = v2 * a, q3 = cs;
+  float inv = 1.0f / fmaxf(sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3), 1e-12f);
+  float qx = q0 * inv, qy = q1 * inv, qz = q2 * inv, qw = q3 * inv;
+  float tx = 2.f * qx, ty = 2.f * qy, tz = 2.f * qz;
+  float twx = tx * qw, twy = ty * qw, twz = tz * qw;
+  float txx = tx * qx, txy = ty * qx, txz = tz * qx;
+  float tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  float r00 = 1.f - (tyy + tzz), r01 = txy - twz, r02 = txz + twy;
+  float r10 = txy + twz, r11 = 1.f - (txx + tzz), r12 = tyz - twx;
+  float r20 = txz - twy, r21 = tyz + twx, r22 = 1.f - (txx + tyy);
+  float y0 = x[0] - h9[3], y1 = x[1] - h9[4], y2 = x[2] - h9[5];
+  out[0] = y0 * r00 + y1 * r10 + y2 * r20 + h9[3] + h9[6];
+  out[1] = y0 * r01 + y1 * r11 + y2 * r21 + h9[4] + h9[7];
+  out[2] = y0 * r02 + y1 * r12 + y2 * r22 + h9[5] + h9[8];
+}
+
+// backward of the quaternion head: g = dL/d out (3).  d9 = dL/d{v,s,t}; dxin = dL/dx.
+__device__ __forceinline__ void nof_quat_backward(const float* h9, const float* x, const float* g, float* d9,
+                                                  float* dxin) {
+  float v0 = h9[0], v1 = h9[1], v2 = h9[2];
+  float nraw = sqrtf(v0 * v0 + v1 * v1 + v2 * v2);
+  bool clamped = nraw < 1e-8f;
+  float n = fmaxf(nraw, 1e-8f);
+  float sn, cs;
+  sincosf(n, &sn, &cs);
+  float a = sn / n;
+  float q[4] = {v0 * a, v1 * a, v2 * a, cs};
+  float qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+  float inv = 1.0f / qn;
+  float qx = q[0] * inv, qy = q[1] * inv, qz = q[2] * inv, qw = q[3] * inv;
+  float r00 = 1.f - 2.f * (qy * qy + qz * qz), r01 = 2.f * (qx * qy - qw * qz), r02 = 2.f * (qx * qz + qw * qy);
+  float r10 = 2.f * (qx * qy + qw * qz), r11 = 1.f - 2.f * (qx * qx + qz * qz), r12 = 2.f * (qy * qz - qw * qx);
+  float r20 = 2.f * (qx * qz - qw * qy), r21 = 2.f * (qy * qz + qw * qx), r22 = 1.f - 2.f * (qx * qx + qy * qy);
+  float y0 = x[0] - h9[3], y1 = x[1] - h9[4], y2 = x[2] - h9[5];
+  // out_j = sum_i y_i R_ij + s_j + t_j
+  float dy0 = r00 * g[0] + r01 * g[1] + r02 * g[2];
+  float dy1 = r10 * g[0] + r11 * g[1] + r12 * g[2];
+  float dy2 = r20 * g[0] + r21 * g[1] + r22 * g[2];
+  dxin[0] = dy0; dxin[1] = dy1; dxin[2] = dy2;
+  d9[3] = g[0] - dy0; d9[4] = g[1] - dy1; d9[5] = g[2] - dy2;  // d s
+  d9[6] = g[0]; d9[7] = g[1]; d9[8] = g[2];                    // d t
+  // dR_ij = y_i g_j
+  float d00 = y0 * g[0], d01 = y0 * g[1], d02 = y0 * g[2];
+  float d10 = y1 * g[0], d11 = y1 * g[1], d12 = y1 * g[2];
+  float d20 = y2 * g[0], d21 = y2 * g[1], d22 = y2 * g[2];
+  // gradient w.r.t. the unit quaternion (x,y,z,w)
+  float gx = 2.f * (qy * (d01 + d10) + qz * (d02 + d20) - 2.f * qx * (d11 + d22) + qw * (d21 - d12));
+  float gy = 2.f * (qx * (d01 + d10) + qz * (d12 + d21) - 2.f * qy * (d00 + d22) + qw * (d02 - d20));
+  float gz = 2.f * (qx * (d02 + d20) + qy * (d12 + d21) - 2.f * qz * (d00 + d11) + qw * (d10 - d01));
+  float gw = 2.f * (qz * (d10 - d01) + qy * (d02 - d20) + qx * (d21 - d12));
+  // through the normalisation q_hat = q/|q|
+  float dot = qx * gx + qy * gy + qz * gz + qw * gw;
+  float e0 = (gx - qx * dot) * inv, e1 = (gy - qy * dot) * inv, e2 = (gz - qz * dot) * inv, e3 = (gw - qw * dot) * inv;
+  // q = (v a(n), cos n), a = sin(n)/n
+  d9[0] = a * e0; d9[1] = a * e1; d9[2] = a * e2;
+  if (!clamped) {
+    float dadn = (n < 1e-2f) ? (-n / 3.0f + n * n * n / 30.0f) : (n * cs - sn) / (n * n);
+    float vd = v0 * e0 + v1 * e1 + v2 * e2;
+    float coef = (vd * dadn - e3 * sn) / n;
+    d9[0] += coef * v0; d9[1] += coef * v1; d9[2] += coef * v2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the chain kernel
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ mcf_chain_params_t p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using L = Smem<W>;
+  Tables& tab = *reinterpret_cast<Tables*>(smem + L::off_tab);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) atomicExch(&g_mcf_device_error, 0xA11C0000u);
+    return;
+  }
+
+  // ---- one-time setup ----
+  {
+    const uint32_t* src_c = reinterpret_cast<const uint32_t*>(p.chunks);
+    uint32_t* dst_c = reinterpret_cast<uint32_t*>(tab.chunks);
+    for (int i = threadIdx.x; i < p.n_chunks * 4; i += kThreads) dst_c[i] = src_c[i];
+    const uint32_t* src_r = reinterpret_cast<const uint32_t*>(p.rounds);
+    uint32_t* dst_r = reinterpret_cast<uint32_t*>(tab.rounds);
+    for (int i = threadIdx.x; i < p.n_rounds * 8; i += kThreads) dst_r[i] = src_r[i];
+    uint4* x0z = reinterpret_cast<uint4*>(smem + L::off_x0);
+    for (int i = threadIdx.x; i < (int)(2 * kBlk / 16); i += kThreads) x0z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&tab.w_full[s], 1);
+      mbar_init(&tab.w_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tab.act_ready[s], 128);
+      mbar_init(&tab.acc_full[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&tab.tmem_base, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tab.tmem_base;
+
+  const long long n_tiles = (p.n_rows + MCF_TILE_ROWS - 1) / MCF_TILE_ROWS;
+  const long long n_pairs = (n_tiles + 1) / 2;
+
+  if (warp == 0) {
+    // =========================== weight producer ===========================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack);
+      for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        for (int r = 0; r < p.n_rounds; ++r) {
+          const int cb = tab.rounds[r].chunk_begin, ce = tab.rounds[r].chunk_end;
+          for (int s = 0; s < 2; ++s) {
+            if (2 * pair + s >= n_tiles) continue;
+            for (int c = cb; c < ce; ++c) {
+              mbar_wait(&tab.w_empty[stage], phase ^ 1u, 0x100u | stage);
+              const uint32_t bytes = tab.chunks[c].bytes;
+              mbar_arrive_expect_tx(&tab.w_full[stage], bytes);
+              bulk_g2s(smem + L::off_ring + stage * kBlk, wsrc + tab.chunks[c].src_off, bytes, &tab.w_full[stage]);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t ar_phase[2] = {0u, 0u};
+      const uint32_t h_addr = smem_u32(smem + L::off_h), x0_addr = smem_u32(smem + L::off_x0);
+      const uint32_t ring_addr = smem_u32(smem + L::off_ring);
+      for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        for (int r = 0; r < p.n_rounds; ++r) {
+          const int cb = tab.rounds[r].chunk_begin, ce = tab.rounds[r].chunk_end;
+          for (int s = 0; s < 2; ++s) {
+            if (2 * pair + s >= n_tiles) continue;
+            mbar_wait(&tab.act_ready[s], ar_phase[s], 0x200u | s);
+            ar_phase[s] ^= 1u;
+            tc_fence_after();
+            for (int c = cb; c < ce; ++c) {
+              mbar_wait(&tab.w_full[stage], phase, 0x300u | stage);
+              tc_fence_after();
+              const mcf_chunk_t ch = tab.chunks[c];
+              const uint32_t a_base = (ch.a_buf ? (h_addr + s * L::kHBytes) : (x0_addr + s * kBlk)) + ch.a_kblock * kBlk;
+              const uint32_t b_base = ring_addr + stage * kBlk;
+              const uint32_t idesc = make_idesc(ch.n);
+              const uint32_t d_tmem = tmem_base + s * kSlotCols + ch.acc_col;
+              for (uint32_t k = 0; k < ch.ksteps; ++k) {
+                const uint64_t ad = make_sdesc(a_base + k * 32u, 0u, 1024u);
+                const uint64_t bd = make_sdesc(b_base + k * 32u, 0u, 1024u);
+                umma_bf16(d_tmem, ad, bd, idesc, (k > 0u || !(ch.flags & 1u)) ? 1u : 0u);
+              }
+              umma_commit(&tab.w_empty[stage]);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(&tab.acc_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue groups ===========================
+    const int s = (warp - 4) >> 2;          // slot
+    const int qtr = warp & 3;               // TMEM lane quarter this warp may access
+    const uint32_t row = qtr * 32 + lane;   // tile row owned by this thread
+    const int gtid = threadIdx.x - 128 - s * 128;
+    uint8_t* hbuf = smem + L::off_h + s * L::kHBytes;
+    uint8_t* x0buf = smem + L::off_x0 + s * kBlk;
+    const uint32_t t_row = tmem_base + ((uint32_t)(qtr * 32) << 16) + s * kSlotCols;
+    const bool saving = p.save != nullptr;
+    uint32_t af_phase = 0;
+    bool store_pending = false;
+
+    for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const long long tile = 2 * pair + s;
+      if (tile >= n_tiles) break;
+      const long long m = tile * MCF_TILE_ROWS + row;
+      const bool valid = m < p.n_rows;
+      const long long mc = valid ? m : (p.n_rows - 1);
+      const long long ray = mc / p.rows_per_ray;
+      uint8_t* save_tile = saving ? reinterpret_cast<uint8_t*>(p.save) + tile * p.save_tile_bytes : nullptr;
+      RowState st;
+      st.sigma = 0.f; st.dx[0] = st.dx[1] = st.dx[2] = 0.f;
+      st.aux[0] = st.aux[1] = st.aux[2] = st.aux[3] = 0.f;
+
+      // make sure an earlier bulk store no longer reads the buffers we are about to overwrite
+      if (store_pending) {
+        if (gtid == 0) bulk_wait_read_all();
+        named_bar_sync(1 + s, 128);
+        store_pending = false;
+      }
+
+      // ------------------------- prologue: build the first operand -------------------------
+      if (p.prologue == MCF_PRO_PE_XYZ) {
+        float x[3] = {0.f, 0.f, 0.f};
+        if (valid) { x[0] = p.xyz[m * 3 + 0]; x[1] = p.xyz[m * 3 + 1]; x[2] = p.xyz[m * 3 + 2]; }
+        __nv_bfloat16* xr = reinterpret_cast<__nv_bfloat16*>(x0buf);
+        auto put = [&](int ch, float v) {
+          uint32_t off = sw128_off(row, (uint32_t)ch >> 3) + ((uint32_t)ch & 7u) * 2u;
+          *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(xr) + off) = __float2bfloat16_rn(v);
+        };
+#pragma unroll
+        for (int c = 0; c < 3; ++c) put(c, x[c]);
+        for (int k = 0; k < p.pe_n_freqs; ++k) {
+          const float f = p.pe_freq[k], w = p.pe_weight[k];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float sn, cs;
+            sincosf(f * x[c], &sn, &cs);
+            put(3 + 6 * k + c, w * sn);
+            put(3 + 6 * k + 3 + c, w * cs);
+          }
+        }
+      } else if (p.prologue == MCF_PRO_DENSE) {
+        const float* src = p.dense + mc * p.dense_stride;
+        for (int c8 = 0; c8 < 8; ++c8) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            int c = c8 * 8 + j;
+            f[j] = (valid && c < p.dense_cols) ? src[c] : 0.f;
+          }
+          uint4 v;
+          v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+          v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(x0buf + sw128_off(row, c8)) = v;
+        }
+      } else if (p.prologue == MCF_PRO_B_NERF) {
+        // backward through rgb = sigmoid(W_rgb he + b) and he = relu(.)   (models/nerf.py:98-99)
+        float4 g = valid ? *reinterpret_cast<const float4*>(p.g_out + m * 4) : make_float4(0, 0, 0, 0);
+        float4 o = valid ? *reinterpret_cast<const float4*>(p.fwd_out + m * 4) : make_float4(0, 0, 0, 0);
+        float d0 = g.x * o.x * (1.f - o.x), d1 = g.y * o.y * (1.f - o.y), d2 = g.z * o.z * (1.f - o.z);
+        st.sigma = g.w;
+        if (valid && p.d_head) *reinterpret_cast<float4*>(p.d_head + m * 4) = make_float4(d0, d1, d2, g.w);
+        const mcf_round_t& r0 = tab.rounds[0];
+        const int nhe = W / 2;
+        const float* wrgb = p.consts + r0.aux_off;  // [3][W/2]
+        const uint32_t* mk = p.fwd_masks + tile * p.fwd_mask_tile_words + r0.mask_off;
+        for (int c0 = 0; c0 < nhe; c0 += 32) {
+          float w0[32], w1[32], w2[32], f[32];
+          load32f(wrgb + c0, w0);
+          load32f(wrgb + nhe + c0, w1);
+          load32f(wrgb + 2 * nhe + c0, w2);
+          const uint32_t word = mk[(c0 >> 5) * 128 + row];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = d0 * w0[j] + d1 * w1[j] + d2 * w2[j];
+            f[j] = ((word >> j) & 1u) ? v : 0.f;
+          }
+          store_h32(hbuf, row, c0, f);
+        }
+      } else {  // MCF_PRO_B_NOF
+        float g[3] = {0.f, 0.f, 0.f}, hs[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) hs[j] = 0.f;
+        if (valid) {
+          g[0] = p.g_out[m * 3 + 0]; g[1] = p.g_out[m * 3 + 1]; g[2] = p.g_out[m * 3 + 2];
+          const float4* hp = reinterpret_cast<const float4*>(p.head_save + m * 12);
+          float4 a = hp[0], b = hp[1], c = hp[2];
+          hs[0] = a.x; hs[1] = a.y; hs[2] = a.z; hs[3] = a.w; hs[4] = b.x; hs[5] = b.y;
+          hs[6] = b.z; hs[7] = b.w; hs[8] = c.x; hs[9] = c.y; hs[10] = c.z; hs[11] = c.w;
+        }
+        float d16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) d16[j] = 0.f;
+        if (p.use_quat) {
+          nof_quat_backward(hs, hs + 9, g, d16, st.dx);
+        } else {  // out = head3 + x   (models/nof.py:82)
+          d16[0] = g[0]; d16[1] = g[1]; d16[2] = g[2];
+          st.dx[0] = g[0]; st.dx[1] = g[1]; st.dx[2] = g[2];
+        }
+        uint4 v;
+        v.x = pack_bf16x2(d16[0], d16[1]); v.y = pack_bf16x2(d16[2], d16[3]);
+        v.z = pack_bf16x2(d16[4], d16[5]); v.w = pack_bf16x2(d16[6], d16[7]);
+        store_h8(hbuf, row, 0, v);
+        v.x = pack_bf16x2(d16[8], d16[9]); v.y = pack_bf16x2(d16[10], d16[11]);
+        v.z = pack_bf16x2(d16[12], d16[13]); v.w = pack_bf16x2(d16[14], d16[15]);
+        store_h8(hbuf, row, 8, v);
+      }
+      fence_proxy_async_smem();
+      if (saving && p.x0_save_off != kNone) {
+        // the prologue's operand is itself needed by the weight-gradient GEMM: store its image
+        named_bar_sync(1 + s, 128);
+        if (gtid == 0) {
+          const bool fwd = p.prologue == MCF_PRO_PE_XYZ || p.prologue == MCF_PRO_DENSE;
+          const uint32_t nbytes = fwd ? kBlk : (p.prologue == MCF_PRO_B_NERF ? (uint32_t)(W / 2 / 64) * kBlk : kBlk);
+          bulk_s2g(save_tile + p.x0_save_off, fwd ? x0buf : hbuf, nbytes);
+          bulk_commit();
+        }
+        store_pending = true;
+      }
+      mbar_arrive(&tab.act_ready[s]);
+
+      // ------------------------------- rounds -------------------------------
+      for (int r = 0; r < p.n_rounds; ++r) {
+        const mcf_round_t rd = tab.rounds[r];
+        mbar_wait(&tab.acc_full[s], af_phase, 0x400u | s);
+        af_phase ^= 1u;
+        tc_fence_after();
+        const bool writes_h = rd.epi != MCF_EPI_NOF_HEAD && rd.epi != MCF_EPI_B_DPE &&
+                              !(rd.epi == MCF_EPI_NERF_RGB && !saving);
+        if (writes_h && store_pending) {
+          if (gtid == 0) bulk_wait_read_all();
+          named_bar_sync(1 + s, 128);
+          store_pending = false;
+        }
+        const uint32_t t_acc = t_row + rd.acc_col;
+        const float* bias_p = (rd.raybias >= 0) ? (p.raybias[rd.raybias] + ray * rd.n_out) : (p.consts + rd.const_off);
+
+        if (rd.epi == MCF_EPI_RELU || rd.epi == MCF_EPI_RELU_SIGMA || rd.epi == MCF_EPI_LINEAR) {
+          float sig = 0.f;
+          for (int c0 = 0; c0 < rd.n_out; c0 += 32) {
+            uint32_t v[32];
+            float f[32], b[32];
+            tmem_ld32(t_acc + c0, v);
+            load32f(bias_p + c0, b);
+            tmem_ld_wait();
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float t = __uint_as_float(v[j]) + b[j];
+              if (rd.epi != MCF_EPI_LINEAR) t = fmaxf(t, 0.f);
+              word |= (t > 0.f ? 1u : 0u) << j;
+              f[j] = t;
+            }
+            if (rd.epi == MCF_EPI_RELU_SIGMA) {
+              float ws[32];
+              load32f(p.consts + rd.aux_off + c0, ws);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sig = fmaf(f[j], ws[j], sig);
+            }
+            store_h32(hbuf, row, c0, f);
+            if (p.masks && rd.mask_off != kNone)
+              p.masks[tile * p.mask_tile_words + rd.mask_off + (c0 >> 5) * 128 + row] = word;
+          }
+          if (rd.epi == MCF_EPI_RELU_SIGMA) {
+            st.sigma = sig + __ldg(p.consts + rd.aux_off + rd.n_out);
+            if (p.sigma_col == 0 && valid) p.out[m * p.out_stride] = st.sigma;  // sigma-only program
+          }
+        } else if (rd.epi == MCF_EPI_NERF_RGB) {
+          const int nhe = rd.n_out;
+          const float* wrgb = p.consts + rd.aux_off;  // [3][nhe] then b_rgb[3]
+          float a0 = __ldg(wrgb + 3 * nhe + 0), a1 = __ldg(wrgb + 3 * nhe + 1), a2 = __ldg(wrgb + 3 * nhe + 2);
+          for (int c0 = 0; c0 < nhe; c0 += 32) {
+            uint32_t v[32];
+            float f[32], b[32], w0[32];
+            tmem_ld32(t_acc + c0, v);
+            load32f(bias_p + c0, b);
+            tmem_ld_wait();
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float t = fmaxf(__uint_as_float(v[j]) + b[j], 0.f);
+              word |= (t > 0.f ? 1u : 0u) << j;
+              f[j] = t;
+            }
+            load32f(wrgb + c0, w0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a0 = fmaf(f[j], w0[j], a0);
+            load32f(wrgb + nhe + c0, w0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a1 = fmaf(f[j], w0[j], a1);
+            load32f(wrgb + 2 * nhe + c0, w0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a2 = fmaf(f[j], w0[j], a2);
+            if (saving) store_h32(hbuf, row, c0, f);
+            if (p.masks && rd.mask_off != kNone)
+              p.masks[tile * p.mask_tile_words + rd.mask_off + (c0 >> 5) * 128 + row] = word;
+          }
+          if (valid) {
+            float4 o;
+            o.x = 1.f / (1.f + __expf(-a0));
+            o.y = 1.f / (1.f + __expf(-a1));
+            o.z = 1.f / (1.f + __expf(-a2));
+            o.w = st.sigma;
+            *reinterpret_cast<float4*>(p.out + m * 4) = o;
+          }
+        } else if (rd.epi == MCF_EPI_NOF_HEAD) {
+          uint32_t v[16];
+          tmem_ld16(t_acc, v);
+          tmem_ld_wait();
+          float h9[9], x[3] = {0.f, 0.f, 0.f}, o[3];
+#pragma unroll
+          for (int j = 0; j < 9; ++j) h9[j] = __uint_as_float(v[j]) + __ldg(bias_p + j);
+          if (valid) { x[0] = p.xyz[m * 3 + 0]; x[1] = p.xyz[m * 3 + 1]; x[2] = p.xyz[m * 3 + 2]; }
+          if (p.use_quat) {
+            nof_quat_apply(h9, x, o);
+          } else {
+            o[0] = h9[0] + x[0]; o[1] = h9[1] + x[1]; o[2] = h9[2] + x[2];
+          }
+          if (valid) {
+            p.out[m * 3 + 0] = o[0]; p.out[m * 3 + 1] = o[1]; p.out[m * 3 + 2] = o[2];
+            if (p.head_save) {
+              float4* hp = reinterpret_cast<float4*>(p.head_save + m * 12);
+              hp[0] = make_float4(h9[0], h9[1], h9[2], h9[3]);
+              hp[1] = make_float4(h9[4], h9[5], h9[6], h9[7]);
+              hp[2] = make_float4(h9[8], x[0], x[1], x[2]);
+            }
+          }
+        } else if (rd.epi == MCF_EPI_B_MASK || rd.epi == MCF_EPI_B_MASK_SIGMA || rd.epi == MCF_EPI_B_LINEAR) {
+          const uint32_t* mk = (rd.mask_off != kNone) ? (p.fwd_masks + tile * p.fwd_mask_tile_words + rd.mask_off) : nullptr;
+          for (int c0 = 0; c0 < rd.n_out; c0 += 32) {
+            uint32_t v[32];
+            float f[32];
+            tmem_ld32(t_acc + c0, v);
+            const uint32_t word = mk ? mk[(c0 >> 5) * 128 + row] : 0xFFFFFFFFu;
+            tmem_ld_wait();
+            if (rd.epi == MCF_EPI_B_MASK_SIGMA) {
+              float ws[32];
+              load32f(p.consts + rd.aux_off + c0, ws);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaf(st.sigma, ws[j], __uint_as_float(v[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = ((word >> j) & 1u) ? f[j] : 0.f;
+            store_h32(hbuf, row, c0, f);
+          }
+        } else if (rd.epi == MCF_EPI_B_DPE) {
+          // d_xyz += J_PE(x)^T dPE, with sin/cos taken from the saved first-layer operand image
+          const uint8_t* x0img = reinterpret_cast<const uint8_t*>(p.fwd_save) + tile * p.fwd_save_tile_bytes + p.fwd_x0_off;
+          float pe[64];
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            uint4 t = *reinterpret_cast<const uint4*>(x0img + sw128_off(row, c8));
+            pe[c8 * 8 + 0] = bf16_lo(t.x); pe[c8 * 8 + 1] = bf16_hi(t.x);
+            pe[c8 * 8 + 2] = bf16_lo(t.y); pe[c8 * 8 + 3] = bf16_hi(t.y);
+            pe[c8 * 8 + 4] = bf16_lo(t.z); pe[c8 * 8 + 5] = bf16_hi(t.z);
+            pe[c8 * 8 + 6] = bf16_lo(t.w); pe[c8 * 8 + 7] = bf16_hi(t.w);
+          }
+          uint32_t v0[32], v1[32];
+          tmem_ld32(t_acc, v0);
+          tmem_ld32(t_acc + 32, v1);
+          tmem_ld_wait();
+          float dpe[64];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { dpe[j] = __uint_as_float(v0[j]); dpe[32 + j] = __uint_as_float(v1[j]); }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) st.dx[c] += dpe[c];
+#pragma unroll
+          for (int k = 0; k < 10; ++k) {
+            if (k < p.pe_n_freqs) {
+              const float f = p.pe_freq[k];
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const int is = 3 + 6 * k + c, ic = is + 3;
+                st.dx[c] += f * (pe[ic] * dpe[is] - pe[is] * dpe[ic]);
+              }
+            }
+          }
+          if (rd.aux_off == 1u && valid && p.d_xyz) {
+            p.d_xyz[m * 3 + 0] = st.dx[0]; p.d_xyz[m * 3 + 1] = st.dx[1]; p.d_xyz[m * 3 + 2] = st.dx[2];
+          }
+        }
+
+        tc_fence_before();
+        if (writes_h) {
+          fence_proxy_async_smem();
+          if (saving && rd.save_off != kNone) {
+            named_bar_sync(1 + s, 128);
+            if (gtid == 0) {
+              bulk_s2g(save_tile + rd.save_off, hbuf, ((uint32_t)rd.n_out + 63u) / 64u * kBlk);
+              bulk_commit();
+            }
+            store_pending = true;
+          }
+        }
+        if (r + 1 < p.n_rounds) mbar_arrive(&tab.act_ready[s]);
+      }
+    }
+    if (gtid == 0) bulk_wait_all();
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packer: fp32 nn.Linear tensors -> bf16 128B-swizzled chunk images / fp32 constants
+// ---------------------------------------------------------------------------------------------
+struct PackPtrs {
+  const float* t[MCF_MAX_PACK_TENSORS];
+};
+
+__global__ void k_pack(const mcf_pack_t* __restrict__ table, PackPtrs ptrs, uint8_t* __restrict__ wpack,
+                       float* __restrict__ consts) {
+  const mcf_pack_t e = table[blockIdx.x];
+  const float* src = ptrs.t[e.tensor];
+  if (e.kind == 1) {
+    for (uint32_t i = threadIdx.x; i < e.bytes; i += blockDim.x) {
+      int r = (int)(i / (uint32_t)max(e.ncols, 1)), c = (int)(i % (uint32_t)max(e.ncols, 1));
+      float v = 0.f;
+      if (r < e.nrows && c < e.ncols) v = src[(long long)(e.row0 + r) * e.ld + e.col0 + c];
+      consts[e.dst_off + i] = v;
+    }
+    return;
+  }
+  const uint32_t rows = e.bytes / 128u;
+  for (uint32_t i = threadIdx.x; i < rows * 8u; i += blockDim.x) {
+    const uint32_t r = i >> 3, c16 = i & 7u;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = (int)c16 * 8 + j;
+      float v = 0.f;
+      if ((int)r < e.nrows && c < e.ncols) {
+        v = e.transposed ? src[(long long)(e.col0 + c) * e.ld + e.row0 + (int)r]
+                         : src[(long long)(e.row0 + (int)r) * e.ld + e.col0 + c];
+      }
+      f[j] = v;
+    }
+    uint4 v;
+    v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+    v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(wpack + e.dst_off + sw128_off(r, c16)) = v;
+  }
+}
+
+}  // namespace mcf
+
+extern "C" {
+
+int mcf_abi_version(void) { return MCF_ABI_VERSION; }
+
+int mcf_device_error_flag(unsigned int* flag_host) {
+  cudaError_t e = cudaDeviceSynchronize();
+  unsigned int v = 0, zero = 0;
+  cudaError_t e2 = cudaMemcpyFromSymbol(&v, mcf::g_mcf_device_error, sizeof(v));
+  if (e2 == cudaSuccess) cudaMemcpyToSymbol(mcf::g_mcf_device_error, &zero, sizeof(zero));
+  if (flag_host) *flag_host = v;
+  if (e != cudaSuccess) return (int)e;
+  if (e2 != cudaSuccess) return (int)e2;
+  return v ? MCF_ERR_DEVICE_FLAG : 0;
+}
+
+int mcf_pack(const mcf_pack_t* table_dev, int n_entries, const float* const* tensors_host, int n_tensors, void* wpack,
+             float* consts, cudaStream_t stream) {
+  if (n_entries <= 0) return 0;
+  if (n_tensors > MCF_MAX_PACK_TENSORS || n_tensors < 0) return MCF_ERR_BAD_ARG;
+  mcf::PackPtrs ptrs;
+  for (int i = 0; i < MCF_MAX_PACK_TENSORS; ++i) ptrs.t[i] = i < n_tensors ? tensors_host[i] : nullptr;
+  mcf::k_pack<<<n_entries, 256, 0, stream>>>(table_dev, ptrs, reinterpret_cast<uint8_t*>(wpack), consts);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+int mcf_chain_launch(const mcf_chain_params_t* pp, cudaStream_t stream) {
+  if (!pp) return MCF_ERR_BAD_ARG;
+  const mcf_chain_params_t& p = *pp;
+  if (p.n_rows <= 0) return 0;
+  if (p.n_chunks <= 0 || p.n_chunks > mcf::kMaxChunks || p.n_rounds <= 0 || p.n_rounds > mcf::kMaxRounds)
+    return MCF_ERR_BAD_ARG;
+  if (p.rows_per_ray <= 0 || p.pe_n_freqs > 10 || p.pe_n_freqs < 0) return MCF_ERR_BAD_ARG;
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int)e;
+  }
+  long long n_tiles = (p.n_rows + MCF_TILE_ROWS - 1) / MCF_TILE_ROWS;
+  long long n_pairs = (n_tiles + 1) / 2;
+  int cap = p.max_ctas > 0 ? p.max_ctas : n_sm;
+  int grid = (int)(n_pairs < cap ? n_pairs : cap);
+  cudaError_t e;
+  if (p.width == 256) {
+    const int smem = (int)mcf::Smem<256>::total;
+    e = cudaFuncSetAttribute(mcf::k_chain<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    mcf::k_chain<256><<<grid, mcf::kThreads, smem, stream>>>(p);
+  } else if (p.width == 128) {
+    const int smem = (int)mcf::Smem<128>::total;
+    e = cudaFuncSetAttribute(mcf::k_chain<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    mcf::k_chain<128><<<grid, mcf::kThreads, smem, stream>>>(p);
+  } else {
+    return MCF_ERR_UNSUPPORTED;
+  }
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // extern "C"

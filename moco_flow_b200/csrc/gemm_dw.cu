@@ -1,0 +1,178 @@
+// Weight-gradient GEMM of the MLP backward on tcgen05:  C[i][j] += sum_rows P[row][i] * Q[row][j].
+//
+// P (= dY of a layer) and Q (= the layer's input) are the bf16 128B-swizzled tile images the chain
+// kernels saved ([128 rows][64 cols] blocks).  The contraction runs over rows, so both operands are
+// consumed MN-major straight from those images -- no transpose pass.  A CTA owns one 128-wide i-block
+// and all j (<=256) and a slice of the row tiles (split-K); accumulators stay in TMEM for the whole
+// slice and are reduced into C with vector fp32 atomics.  Optionally an extra N=64 MMA against a
+// ones-tile produces colsum_p[i] = sum_rows P[row][i] (the bias gradient).
+// Reference semantics: autograd of nn.Linear (models/nerf.py:30-58, models/nof.py:42-53).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/moco_flow_b200.h"
+#include "ptx.cuh"
+
+namespace mcf {
+
+constexpr int kDwThreads = 256;
+constexpr int kDwStages = 2;
+constexpr uint32_t kBlkD = MCF_BLOCK_BYTES;
+constexpr uint32_t kStageBytes = 2 * kBlkD + 4 * kBlkD;  // P i-block (128 cols) + Q (<=256 cols)
+
+struct DwCtl {
+  uint64_t full[kDwStages];
+  uint64_t empty[kDwStages];
+  uint64_t done;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+constexpr uint32_t kDwOffOnes = kDwStages * kStageBytes;
+constexpr uint32_t kDwOffCtl = kDwOffOnes + kBlkD;
+constexpr uint32_t kDwSmem = kDwOffCtl + sizeof(DwCtl);
+
+__global__ void __launch_bounds__(kDwThreads, 1) k_dw(const __grid_constant__ mcf_dw_params_t p, int nib) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  DwCtl& ctl = *reinterpret_cast<DwCtl*>(smem + kDwOffCtl);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) atomicExch(&g_mcf_device_error, 0xA11C0001u);
+    return;
+  }
+  const int ib = blockIdx.x % nib;
+  const int split = blockIdx.x / nib, nsplit = gridDim.x / nib;
+  const uint32_t q_blocks = (uint32_t)(p.q_cols + 63) / 64;
+  const uint32_t n_mma = q_blocks * 64u;  // whole 64-column atoms only (canonical MN-major SW128 shapes)
+  const bool want_colsum = p.colsum_p != nullptr;
+
+  // ones tile: column 0 of every row = 1.0 (bf16), rest 0
+  for (int i = threadIdx.x; i < (int)(kBlkD / 16); i += kDwThreads)
+    reinterpret_cast<uint4*>(smem + kDwOffOnes)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (threadIdx.x < 128)
+    *reinterpret_cast<uint16_t*>(smem + kDwOffOnes + sw128_off(threadIdx.x, 0)) = 0x3F80u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDwStages; ++s) {
+      mbar_init(&ctl.full[s], 1);
+      mbar_init(&ctl.empty[s], 1);
+    }
+    mbar_init(&ctl.done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&ctl.tmem_base, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl.tmem_base;
+
+  long long my_tiles = 0;
+  for (long long t = split; t < p.n_tiles; t += nsplit) ++my_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint8_t* pb = reinterpret_cast<const uint8_t*>(p.p_base);
+      const uint8_t* qb = reinterpret_cast<const uint8_t*>(p.q_base);
+      for (long long t = split; t < p.n_tiles; t += nsplit) {
+        mbar_wait(&ctl.empty[stage], phase ^ 1u, 0x500u | stage);
+        mbar_arrive_expect_tx(&ctl.full[stage], 2 * kBlkD + q_blocks * kBlkD);
+        uint8_t* dst = smem + stage * kStageBytes;
+        bulk_g2s(dst, pb + t * p.p_tile_bytes + p.p_off + (uint32_t)ib * 2u * kBlkD, 2 * kBlkD, &ctl.full[stage]);
+        bulk_g2s(dst + 2 * kBlkD, qb + t * p.q_tile_bytes + p.q_off, q_blocks * kBlkD, &ctl.full[stage]);
+        if (++stage == kDwStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t idesc = make_idesc(n_mma, true, true);
+      const uint32_t idesc1 = make_idesc(64, true, true);
+      const uint32_t ones_addr = smem_u32(smem + kDwOffOnes);
+      bool first = true;
+      for (long long t = split; t < p.n_tiles; t += nsplit) {
+        mbar_wait(&ctl.full[stage], phase, 0x600u | stage);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * kStageBytes);
+        const uint32_t b_base = a_base + 2 * kBlkD;
+        for (uint32_t k = 0; k < 8; ++k) {  // 8 x 16 rows
+          const uint64_t ad = make_sdesc(a_base + k * 2048u, kBlkD, 1024u);
+          const uint64_t bd = make_sdesc(b_base + k * 2048u, kBlkD, 1024u);
+          umma_bf16(tmem_base, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+          if (want_colsum) {
+            const uint64_t od = make_sdesc(ones_addr + k * 2048u, kBlkD, 1024u);
+            umma_bf16(tmem_base + 256, ad, od, idesc1, (first && k == 0) ? 0u : 1u);
+          }
+        }
+        first = false;
+        umma_commit(&ctl.empty[stage]);
+        if (++stage == kDwStages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(&ctl.done);
+    }
+  } else if (warp >= 4 && my_tiles > 0) {
+    const int qtr = warp & 3;
+    const uint32_t row = qtr * 32 + lane;
+    const int i = ib * 128 + (int)row;
+    mbar_wait(&ctl.done, 0u, 0x700u);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(qtr * 32) << 16);
+    for (uint32_t c0 = 0; c0 < n_mma; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(t_row + c0, v);
+      tmem_ld_wait();
+      if (i < p.n_i) {
+        float* dst = p.out + (long long)i * p.ld_out + c0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if ((int)c0 + q * 4 < p.n_j) {  // n_j is padded to a multiple of 4 by the host plan
+            float4 a = make_float4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]),
+                                   __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+            atomicAdd(reinterpret_cast<float4*>(dst + q * 4), a);
+          }
+        }
+      }
+    }
+    if (want_colsum) {
+      uint32_t v[16];
+      tmem_ld16(t_row + 256, v);
+      tmem_ld_wait();
+      if (i < p.n_i) atomicAdd(p.colsum_p + i, __uint_as_float(v[0]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace mcf
+
+extern "C" int mcf_dw_gemm(const mcf_dw_params_t* pp, cudaStream_t stream) {
+  if (!pp) return MCF_ERR_BAD_ARG;
+  const mcf_dw_params_t& p = *pp;
+  if (p.n_tiles <= 0) return 0;
+  if (p.n_i <= 0 || p.n_j <= 0 || p.n_j > 256 || (p.n_j & 3) || (p.ld_out & 3) || p.p_cols % 128 != 0 ||
+      p.n_i > p.p_cols || p.q_cols > 256 || p.n_j > ((p.q_cols + 63) / 64) * 64)
+    return MCF_ERR_BAD_ARG;
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int nib = (p.n_i + 127) / 128;
+  int cap = p.max_ctas > 0 ? p.max_ctas : n_sm;
+  long long nsplit = cap / nib;
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > p.n_tiles) nsplit = p.n_tiles;
+  cudaError_t e = cudaFuncSetAttribute(mcf::k_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mcf::kDwSmem);
+  if (e != cudaSuccess) return (int)e;
+  mcf::k_dw<<<(unsigned)(nsplit * nib), mcf::kDwThreads, mcf::kDwSmem, stream>>>(p, nib);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}

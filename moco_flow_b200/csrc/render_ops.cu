@@ -1,0 +1,664 @@
+// fp32 HBM-bound kernels of the ray-rendering path (compiled with -fmad=false so that the
+// arithmetic is the same sequence of individually rounded fp32 operations the reference's
+// unfused PyTorch ops perform):
+//   * stratified depth sampling + point generation      (models/rendering.py:245-263)
+//   * standalone positional encoding fwd/bwd            (models/embedding.py:42-46)
+//   * per-ray bias folding of per-ray features          (replaces rendering.py:73-75,133-142 cat)
+//   * alpha compositing fwd + analytic bwd              (models/rendering.py:158-190)
+//   * sample_pdf inverse-CDF + sort-merge               (models/rendering.py:5-46, :326)
+//   * masked flow-consistency residual fwd/bwd          (models/rendering.py:304-314,363-373)
+// One warp per ray everywhere; lane-strided (coalesced) sample access; warp-shuffle scans.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/moco_flow_b200.h"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr unsigned kFull = 0xffffffffu;
+
+inline int grid_for_warps(long long n_warps, int warps_per_block = kWarpsPerBlock) {
+  long long b = (n_warps + warps_per_block - 1) / warps_per_block;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+// -------------------------------------------------------------------------------------------------
+// depth sampling + points
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float z_at(float near, float far, float t, int use_disp) {
+  float omt = 1.0f - t;
+  if (!use_disp) return near * omt + far * t;                     // rendering.py:247
+  return 1.0f / ((1.0f / near) * omt + (1.0f / far) * t);         // rendering.py:249
+}
+
+__global__ void k_coarse_samples(const float* __restrict__ rays, int ray_stride, const float* __restrict__ t_steps,
+                                 const float* __restrict__ perturb_rand, float perturb, int use_disp, int R, int S,
+                                 float* __restrict__ z_out, float* __restrict__ xyz_out) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)R * S) return;
+  int r = static_cast<int>(idx / S), i = static_cast<int>(idx - (long long)r * S);
+  const float* ray = rays + (long long)r * ray_stride;
+  float near = ray[6], far = ray[7];
+  float z = z_at(near, far, t_steps[i], use_disp);
+  if (perturb > 0.0f) {  // rendering.py:253-260
+    float lo = z, hi = z;
+    if (i > 0) lo = 0.5f * (z_at(near, far, t_steps[i - 1], use_disp) + z);
+    if (i < S - 1) hi = 0.5f * (z + z_at(near, far, t_steps[i + 1], use_disp));
+    float pr = perturb * perturb_rand[idx];
+    z = lo + (hi - lo) * pr;
+  }
+  z_out[idx] = z;
+  if (xyz_out) {  // rendering.py:262-263
+    xyz_out[idx * 3 + 0] = ray[0] + ray[3] * z;
+    xyz_out[idx * 3 + 1] = ray[1] + ray[4] * z;
+    xyz_out[idx * 3 + 2] = ray[2] + ray[5] * z;
+  }
+}
+
+__global__ void k_points(const float* __restrict__ rays, int ray_stride, const float* __restrict__ z, int R, int S,
+                         float* __restrict__ xyz_out) {  // rendering.py:329-330
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)R * S) return;
+  int r = static_cast<int>(idx / S);
+  const float* ray = rays + (long long)r * ray_stride;
+  float zz = z[idx];
+  xyz_out[idx * 3 + 0] = ray[0] + ray[3] * zz;
+  xyz_out[idx * 3 + 1] = ray[1] + ray[4] * zz;
+  xyz_out[idx * 3 + 2] = ray[2] + ray[5] * zz;
+}
+
+// -------------------------------------------------------------------------------------------------
+// standalone positional encoding
+// -------------------------------------------------------------------------------------------------
+struct PEArgs {
+  int n_freqs;
+  float freq[MCF_MAX_FREQS];
+  float weight[MCF_MAX_FREQS];
+};
+
+__global__ void k_pe_fwd(const float* __restrict__ x, long long B, int C, PEArgs pe, int out_stride,
+                         float* __restrict__ out) {
+  int OC = C * (2 * pe.n_freqs + 1);
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= B * OC) return;
+  long long m = idx / OC;
+  int oc = static_cast<int>(idx - m * OC);
+  float v;
+  if (oc < C) {
+    v = x[m * C + oc];
+  } else {
+    int q = (oc - C) / C, c = (oc - C) - q * C;
+    int k = q >> 1;
+    float arg = pe.freq[k] * x[m * C + c];
+    v = pe.weight[k] * ((q & 1) ? cosf(arg) : sinf(arg));
+  }
+  out[m * out_stride + oc] = v;
+}
+
+// dx[m,c] = dy[m,c] + sum_k w_k f_k (cos(f_k x) dy_sin - sin(f_k x) dy_cos)
+__global__ void k_pe_bwd(const float* __restrict__ x, const float* __restrict__ dy, long long B, int C, PEArgs pe,
+                         int dy_stride, float* __restrict__ dx) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= B * C) return;
+  long long m = idx / C;
+  int c = static_cast<int>(idx - m * C);
+  float xv = x[idx];
+  const float* g = dy + m * dy_stride;
+  float acc = g[c];
+  for (int k = 0; k < pe.n_freqs; ++k) {
+    float s, co;
+    sincosf(pe.freq[k] * xv, &s, &co);
+    float wf = pe.weight[k] * pe.freq[k];
+    acc += wf * (co * g[C + (2 * k) * C + c] - s * g[C + (2 * k + 1) * C + c]);
+  }
+  dx[idx] = acc;
+}
+
+// -------------------------------------------------------------------------------------------------
+// per-ray bias:  out[r, n] = bias[n] + sum_j W[n, col_off + j] * feat[r, j]      (fp32, exact fold of
+// the per-ray constant input columns -- index / direction embeddings -- of a Linear layer)
+// -------------------------------------------------------------------------------------------------
+__global__ void k_ray_bias(const float* __restrict__ W, int w_stride, int col_off, const float* __restrict__ bias,
+                           const float* __restrict__ feat, int feat_stride, int E, int R, int N,
+                           float* __restrict__ out) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)R * N) return;
+  int r = static_cast<int>(idx / N), n = static_cast<int>(idx - (long long)r * N);
+  const float* w = W + (long long)n * w_stride + col_off;
+  const float* f = feat + (long long)r * feat_stride;
+  float acc = bias ? bias[n] : 0.0f;
+  for (int j = 0; j < E; ++j) acc = fmaf(w[j], f[j], acc);
+  out[idx] = acc;
+}
+
+// -------------------------------------------------------------------------------------------------
+// alpha compositing
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_incl_prod(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float n = __shfl_up_sync(kFull, v, o);
+    if (lane >= o) v *= n;
+  }
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float density(float raw, int act) {
+  if (act == MCF_ACT_RELU) return fmaxf(raw, 0.0f);
+  return raw > 20.0f ? raw : log1pf(expf(raw));  // nn.Softplus(beta=1, threshold=20)
+}
+__device__ __forceinline__ float density_grad(float raw, int act) {
+  if (act == MCF_ACT_RELU) return raw > 0.0f ? 1.0f : 0.0f;
+  if (raw > 20.0f) return 1.0f;
+  float e = expf(raw);
+  return e / (e + 1.0f);
+}
+
+// sigma at sigma[m*sigma_stride], rgb (optional) at rgb[m*rgb_stride + 0..2]
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_composite_fwd(const float* __restrict__ sigma, int sigma_stride, const float* __restrict__ rgb, int rgb_stride,
+                const float* __restrict__ z, const float* __restrict__ dirs, int dir_stride,
+                const float* __restrict__ noise, float noise_std, const float* __restrict__ bg, int act, int R, int S,
+                float* __restrict__ weights, float* __restrict__ alphas, float* __restrict__ rgb_out,
+                float* __restrict__ depth_out, float* __restrict__ opacity_out) {
+  int lane = threadIdx.x & 31;
+  int r = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const float* d = dirs + (long long)r * dir_stride;
+  float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);  // rendering.py:164
+  long long base = (long long)r * S;
+  float carry = 1.0f, sw = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f;
+  for (int c = 0; c < S; c += 32) {
+    int i = c + lane;
+    bool ok = i < S;
+    float zi = ok ? z[base + i] : 0.f;
+    float zn = (i + 1 < S) ? z[base + i + 1] : 0.f;
+    float delta = (i + 1 < S) ? (zn - zi) : 1e10f;  // rendering.py:158-160
+    delta = delta * dn;
+    float raw = ok ? sigma[(base + i) * sigma_stride] : 0.f;
+    if (noise && ok) raw = raw + noise[base + i] * noise_std;  // rendering.py:166,170
+    float alpha = ok ? (1.0f - expf(-delta * density(raw, act))) : 0.f;
+    float q = ok ? (1.0f - alpha + 1e-10f) : 1.0f;  // rendering.py:177
+    float incl = warp_incl_prod(q, lane);
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    float T = carry * excl;  // exclusive cumprod, rendering.py:179
+    float w = alpha * T;
+    carry = carry * __shfl_sync(kFull, incl, 31);
+    if (ok) {
+      if (weights) weights[base + i] = w;
+      if (alphas) alphas[base + i] = alpha;
+      sw += w;
+      sd += w * zi;
+      if (rgb) {
+        const float* cc = rgb + (base + i) * rgb_stride;
+        sr += w * cc[0];
+        sg += w * cc[1];
+        sb += w * cc[2];
+      }
+    }
+  }
+  sw = warp_sum(sw);
+  sd = warp_sum(sd);
+  if (rgb) {
+    sr = warp_sum(sr);
+    sg = warp_sum(sg);
+    sb = warp_sum(sb);
+  }
+  if (lane == 0) {
+    if (opacity_out) opacity_out[r] = sw;
+    if (rgb && rgb_out) {
+      float rem = 1.0f - sw;
+      if (bg) {  // rendering.py:189-190
+        sr = sr + bg[r * 3 + 0] * rem;
+        sg = sg + bg[r * 3 + 1] * rem;
+        sb = sb + bg[r * 3 + 2] * rem;
+      }
+      rgb_out[r * 3 + 0] = sr;
+      rgb_out[r * 3 + 1] = sg;
+      rgb_out[r * 3 + 2] = sb;
+    }
+    if (rgb && depth_out) depth_out[r] = sd;
+  }
+}
+
+// Analytic backward (recomputes alpha/T; per-warp smem scratch holds e=exp(-delta*dens), T, delta).
+// d_sigma written at d_sigma[m*ds_stride]; d_rgb (optional) at d_rgb[m*drgb_stride+0..2].
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_composite_bwd(const float* __restrict__ sigma, int sigma_stride, const float* __restrict__ rgb, int rgb_stride,
+                const float* __restrict__ z, const float* __restrict__ dirs, int dir_stride,
+                const float* __restrict__ noise, float noise_std, const float* __restrict__ bg, int act, int R, int S,
+                const float* __restrict__ g_rgb, const float* __restrict__ g_depth, const float* __restrict__ g_opacity,
+                const float* __restrict__ g_weights, float* __restrict__ d_sigma, int ds_stride,
+                float* __restrict__ d_rgb, int drgb_stride) {
+  extern __shared__ float scratch[];
+  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int r = blockIdx.x * kWarpsPerBlock + wib;
+  if (r >= R) return;
+  float* sE = scratch + (size_t)wib * 3 * S;
+  float* sT = sE + S;
+  float* sD = sT + S;
+  const float* d = dirs + (long long)r * dir_stride;
+  float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  long long base = (long long)r * S;
+  float carry = 1.0f;
+  for (int c = 0; c < S; c += 32) {
+    int i = c + lane;
+    bool ok = i < S;
+    float zi = ok ? z[base + i] : 0.f;
+    float zn = (i + 1 < S) ? z[base + i + 1] : 0.f;
+    float delta = ((i + 1 < S) ? (zn - zi) : 1e10f) * dn;
+    float raw = ok ? sigma[(base + i) * sigma_stride] : 0.f;
+    if (noise && ok) raw = raw + noise[base + i] * noise_std;
+    float e = ok ? expf(-delta * density(raw, act)) : 1.0f;
+    float alpha = 1.0f - e;
+    float q = ok ? (1.0f - alpha + 1e-10f) : 1.0f;
+    float incl = warp_incl_prod(q, lane);
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    if (ok) {
+      sE[i] = e;
+      sT[i] = carry * excl;
+      sD[i] = delta;
+    }
+    carry = carry * __shfl_sync(kFull, incl, 31);
+  }
+  __syncwarp();
+  float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, go = 0.f, br = 0.f, bgc = 0.f, bb = 0.f;
+  if (g_rgb) {
+    gr = g_rgb[r * 3 + 0];
+    gg = g_rgb[r * 3 + 1];
+    gb = g_rgb[r * 3 + 2];
+  }
+  if (g_depth) gd = g_depth[r];
+  if (g_opacity) go = g_opacity[r];
+  if (bg) {
+    br = bg[r * 3 + 0];
+    bgc = bg[r * 3 + 1];
+    bb = bg[r * 3 + 2];
+  }
+  float suffix = 0.f;  // sum_{j>i} g_j w_j, carried from the chunks to the right
+  int last_chunk = ((S - 1) / 32) * 32;
+  for (int c = last_chunk; c >= 0; c -= 32) {
+    int i = c + lane;
+    bool ok = i < S;
+    float e = ok ? sE[i] : 1.f, T = ok ? sT[i] : 0.f, delta = ok ? sD[i] : 0.f;
+    float alpha = 1.0f - e;
+    float w = alpha * T;
+    float g = 0.f;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    if (ok) {
+      g = go + gd * z[base + i];
+      if (rgb) {
+        const float* cc = rgb + (base + i) * rgb_stride;
+        c0 = cc[0];
+        c1 = cc[1];
+        c2 = cc[2];
+        g += gr * (c0 - br) + gg * (c1 - bgc) + gb * (c2 - bb);
+      }
+      if (g_weights) g += g_weights[base + i];
+    }
+    float term = g * w;
+    // reverse inclusive scan over lanes
+    float incl = term;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float n = __shfl_down_sync(kFull, incl, o);
+      if (lane + o < 32) incl += n;
+    }
+    float after = suffix + (incl - term);  // strictly to the right of i
+    suffix = suffix + __shfl_sync(kFull, incl, 0);
+    if (ok) {
+      float q = 1.0f - alpha + 1e-10f;
+      float dalpha = g * T - after / q;  // cumprod backward (division form, as autograd)
+      float raw = sigma[(base + i) * sigma_stride];
+      if (noise) raw = raw + noise[base + i] * noise_std;
+      float ddens = dalpha * (delta * e);
+      d_sigma[(base + i) * ds_stride] = ddens * density_grad(raw, act);
+      if (d_rgb) {
+        float* o = d_rgb + (base + i) * drgb_stride;
+        o[0] = w * gr;
+        o[1] = w * gg;
+        o[2] = w * gb;
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// sample_pdf (+ optional sort-merge with the coarse depths)
+// -------------------------------------------------------------------------------------------------
+// Per warp smem: cdf[nb+1] | bins[nb+1] | sort buffer [npow2]
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_sample_pdf(const float* __restrict__ bins, int bins_stride, int bins_are_z, const float* __restrict__ wts,
+             int w_stride, const float* __restrict__ cdf_in, int cdf_stride, const float* __restrict__ u, int u_stride,
+             float eps, int R, int nb, int n_imp, const float* __restrict__ z_coarse, int zc_stride, int n_coarse,
+             int npow2, float* __restrict__ samples, int* __restrict__ inds_out, float* __restrict__ cdf_out,
+             float* __restrict__ z_merged) {
+  extern __shared__ float scratch[];
+  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int r = blockIdx.x * kWarpsPerBlock + wib;
+  if (r >= R) return;
+  int per_warp = 2 * (nb + 1) + npow2;
+  float* s_cdf = scratch + (size_t)wib * per_warp;
+  float* s_bin = s_cdf + (nb + 1);
+  float* s_sort = s_bin + (nb + 1);
+
+  // bins: given, or mid-points of the coarse depths (rendering.py:321)
+  const float* brow = bins + (long long)r * bins_stride;
+  for (int j = lane; j <= nb; j += 32) s_bin[j] = bins_are_z ? 0.5f * (brow[j] + brow[j + 1]) : brow[j];
+
+  if (cdf_in) {
+    const float* crow = cdf_in + (long long)r * cdf_stride;
+    for (int j = lane; j <= nb; j += 32) s_cdf[j] = crow[j];
+  } else {
+    // rendering.py:20-23.  Fixed order: weights+eps in fp32; total accumulated in fp64 and rounded
+    // once; pdf = w/total (IEEE fp32 division); cdf = running fp64 sum of pdf, rounded per element.
+    const float* wrow = wts + (long long)r * w_stride;
+    double part = 0.0;
+    for (int j = lane; j < nb; j += 32) part += static_cast<double>(wrow[j] + eps);
+    float total = static_cast<float>(warp_sum_d(part));
+    double run = 0.0;
+    if (lane == 0) s_cdf[0] = 0.0f;
+    for (int c = 0; c < nb; c += 32) {
+      int j = c + lane;
+      double p = (j < nb) ? static_cast<double>((wrow[j] + eps) / total) : 0.0;
+      double incl = p;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        double n = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += n;
+      }
+      if (j < nb) s_cdf[j + 1] = static_cast<float>(run + incl);
+      run += __shfl_sync(kFull, incl, 31);
+    }
+  }
+  __syncwarp();
+  if (cdf_out) {
+    float* co = cdf_out + (long long)r * (nb + 1);
+    for (int j = lane; j <= nb; j += 32) co[j] = s_cdf[j];
+  }
+
+  const float* urow = u + (long long)r * u_stride;
+  for (int k = lane; k < n_imp; k += 32) {
+    float uk = urow[k];
+    // searchsorted(cdf, u, right=True): first index with cdf[idx] > u, in [0, nb+1]   (:33)
+    int lo = 0, hi = nb + 1;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (s_cdf[mid] <= uk) lo = mid + 1; else hi = mid;
+    }
+    int below = max(lo - 1, 0), above = min(lo, nb);  // :34-35
+    float c0 = s_cdf[below], c1 = s_cdf[above];
+    float b0 = s_bin[below], b1 = s_bin[above];
+    float denom = c1 - c0;
+    if (denom < eps) denom = 1.0f;  // :41-42
+    float s = b0 + (uk - c0) / denom * (b1 - b0);  // :45
+    if (samples) samples[(long long)r * n_imp + k] = s;
+    if (inds_out) inds_out[(long long)r * n_imp + k] = lo;
+    if (z_merged) s_sort[n_coarse + k] = s;
+  }
+  if (!z_merged) return;
+
+  // sort(cat(z_coarse, samples))  (rendering.py:326): in-warp bitonic sort in shared memory
+  const float* zc = z_coarse + (long long)r * zc_stride;
+  for (int j = lane; j < n_coarse; j += 32) s_sort[j] = zc[j];
+  int n_tot = n_coarse + n_imp;
+  for (int j = n_tot + lane; j < npow2; j += 32) s_sort[j] = CUDART_INF_F;
+  __syncwarp();
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < npow2; t += 32) {
+        int p = t ^ j;
+        if (p > t) {
+          float a = s_sort[t], b = s_sort[p];
+          bool up = (t & k) == 0;
+          if ((a > b) == up) {
+            s_sort[t] = b;
+            s_sort[p] = a;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  float* zo = z_merged + (long long)r * n_tot;
+  for (int j = lane; j < n_tot; j += 32) zo[j] = s_sort[j];
+}
+
+// -------------------------------------------------------------------------------------------------
+// masked flow-consistency residual
+// -------------------------------------------------------------------------------------------------
+// stats: [0] masked sum (double), [1] masked count (double), [2] total sum (double)
+__global__ void k_masked_l1_fwd(const float* __restrict__ a, const float* __restrict__ b,
+                                const float* __restrict__ alphas, float thresh, long long M,
+                                float* __restrict__ resid, double* __restrict__ stats) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  float res = 0.f;
+  bool sel = false;
+  if (idx < M) {
+    float d0 = fabsf(a[idx * 3 + 0] - b[idx * 3 + 0]);
+    float d1 = fabsf(a[idx * 3 + 1] - b[idx * 3 + 1]);
+    float d2 = fabsf(a[idx * 3 + 2] - b[idx * 3 + 2]);
+    res = ((d0 + d1) + d2) / 3.0f;  // torch.mean over the 3 coordinates
+    sel = alphas[idx] >= thresh;
+    if (resid) resid[idx] = res;
+  }
+  if (!stats) return;
+  double ms = warp_sum_d(sel ? (double)res : 0.0);
+  double mc = warp_sum_d(sel ? 1.0 : 0.0);
+  double ts = warp_sum_d(idx < M ? (double)res : 0.0);
+  __shared__ double sh[3][32];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+    sh[0][w] = ms;
+    sh[1][w] = mc;
+    sh[2][w] = ts;
+  }
+  __syncthreads();
+  if (w == 0) {
+    int nw = blockDim.x >> 5;
+    ms = warp_sum_d(lane < nw ? sh[0][lane] : 0.0);
+    mc = warp_sum_d(lane < nw ? sh[1][lane] : 0.0);
+    ts = warp_sum_d(lane < nw ? sh[2][lane] : 0.0);
+    if (lane == 0) {
+      atomicAdd(&stats[0], ms);
+      atomicAdd(&stats[1], mc);
+      atomicAdd(&stats[2], ts);
+    }
+  }
+}
+
+// mean over the selected samples (all samples if none is selected): rendering.py:306-311 + torch.mean
+__global__ void k_masked_l1_finalize(const double* __restrict__ stats, long long M, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double v = stats[1] > 0.0 ? stats[0] / stats[1] : stats[2] / (double)M;
+    out[0] = static_cast<float>(v);
+  }
+}
+
+// d_b[m,:] = -sign(a-b)/3 * g_m ;  g_m = g_resid[m] (compat) or g_mean * sel_m / count (fused mean)
+__global__ void k_masked_l1_bwd(const float* __restrict__ a, const float* __restrict__ b,
+                                const float* __restrict__ alphas, float thresh, long long M,
+                                const float* __restrict__ g_resid, const float* __restrict__ g_mean,
+                                const double* __restrict__ stats, float* __restrict__ d_b) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= M) return;
+  float g;
+  if (g_resid) {
+    g = g_resid[idx];
+  } else {
+    double cnt = stats[1];
+    bool sel = cnt > 0.0 ? (alphas[idx] >= thresh) : true;
+    double n = cnt > 0.0 ? cnt : (double)M;
+    g = sel ? static_cast<float>((double)g_mean[0] / n) : 0.f;
+  }
+  g = g / 3.0f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float df = a[idx * 3 + c] - b[idx * 3 + c];
+    float s = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+    d_b[idx * 3 + c] = -s * g;
+  }
+}
+
+inline int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
+PEArgs make_pe(int n_freqs, const float* freqs, const float* weights) {
+  PEArgs a;
+  a.n_freqs = n_freqs;
+  for (int i = 0; i < MCF_MAX_FREQS; ++i) {
+    a.freq[i] = i < n_freqs ? freqs[i] : 0.f;
+    a.weight[i] = i < n_freqs ? weights[i] : 0.f;
+  }
+  return a;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int mcf_coarse_samples(const float* rays, int ray_stride, const float* t_steps, const float* perturb_rand,
+                       float perturb, int use_disp, int n_rays, int n_samples, float* z_out, float* xyz_out,
+                       cudaStream_t stream) {
+  if (n_rays <= 0 || n_samples <= 0) return 0;
+  if (perturb > 0.f && !perturb_rand) return MCF_ERR_BAD_ARG;
+  long long n = (long long)n_rays * n_samples;
+  k_coarse_samples<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rays, ray_stride, t_steps, perturb_rand, perturb,
+                                                                   use_disp, n_rays, n_samples, z_out, xyz_out);
+  return check_launch();
+}
+
+int mcf_ray_points(const float* rays, int ray_stride, const float* z, int n_rays, int n_samples, float* xyz_out,
+                   cudaStream_t stream) {
+  if (n_rays <= 0 || n_samples <= 0) return 0;
+  long long n = (long long)n_rays * n_samples;
+  k_points<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rays, ray_stride, z, n_rays, n_samples, xyz_out);
+  return check_launch();
+}
+
+int mcf_pe_fwd(const float* x, long long n_rows, int in_channels, int n_freqs, const float* freqs_host,
+               const float* weights_host, float* out, int out_stride, cudaStream_t stream) {
+  if (n_freqs > MCF_MAX_FREQS || n_freqs < 0) return MCF_ERR_BAD_ARG;
+  if (n_rows <= 0) return 0;
+  PEArgs pe = make_pe(n_freqs, freqs_host, weights_host);
+  long long n = n_rows * in_channels * (2 * n_freqs + 1);
+  k_pe_fwd<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, n_rows, in_channels, pe, out_stride, out);
+  return check_launch();
+}
+
+int mcf_pe_bwd(const float* x, const float* dy, long long n_rows, int in_channels, int n_freqs,
+               const float* freqs_host, const float* weights_host, int dy_stride, float* dx, cudaStream_t stream) {
+  if (n_freqs > MCF_MAX_FREQS || n_freqs < 0) return MCF_ERR_BAD_ARG;
+  if (n_rows <= 0) return 0;
+  PEArgs pe = make_pe(n_freqs, freqs_host, weights_host);
+  long long n = n_rows * in_channels;
+  k_pe_bwd<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, dy, n_rows, in_channels, pe, dy_stride, dx);
+  return check_launch();
+}
+
+int mcf_ray_bias(const float* W, int w_stride, int col_off, const float* bias, const float* feat, int feat_stride,
+                 int n_feat, int n_rays, int n_out, float* out, cudaStream_t stream) {
+  if (n_rays <= 0 || n_out <= 0) return 0;
+  long long n = (long long)n_rays * n_out;
+  k_ray_bias<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(W, w_stride, col_off, bias, feat, feat_stride, n_feat,
+                                                             n_rays, n_out, out);
+  return check_launch();
+}
+
+int mcf_composite_fwd(const float* sigma, int sigma_stride, const float* rgb, int rgb_stride, const float* z,
+                      const float* dirs, int dir_stride, const float* noise, float noise_std, const float* background,
+                      int activation, int n_rays, int n_samples, float* weights, float* alphas, float* rgb_out,
+                      float* depth_out, float* opacity_out, cudaStream_t stream) {
+  if (activation != MCF_ACT_RELU && activation != MCF_ACT_SOFTPLUS) return MCF_ERR_BAD_ARG;
+  if (n_rays <= 0 || n_samples <= 0) return 0;
+  k_composite_fwd<<<grid_for_warps(n_rays), kWarpsPerBlock * 32, 0, stream>>>(
+      sigma, sigma_stride, rgb, rgb_stride, z, dirs, dir_stride, noise, noise_std, background, activation, n_rays,
+      n_samples, weights, alphas, rgb_out, depth_out, opacity_out);
+  return check_launch();
+}
+
+int mcf_composite_bwd(const float* sigma, int sigma_stride, const float* rgb, int rgb_stride, const float* z,
+                      const float* dirs, int dir_stride, const float* noise, float noise_std, const float* background,
+                      int activation, int n_rays, int n_samples, const float* g_rgb, const float* g_depth,
+                      const float* g_opacity, const float* g_weights, float* d_sigma, int d_sigma_stride, float* d_rgb,
+                      int d_rgb_stride, cudaStream_t stream) {
+  if (activation != MCF_ACT_RELU && activation != MCF_ACT_SOFTPLUS) return MCF_ERR_BAD_ARG;
+  if (n_rays <= 0 || n_samples <= 0) return 0;
+  size_t smem = (size_t)kWarpsPerBlock * 3 * n_samples * sizeof(float);
+  if (smem > 200 * 1024) return MCF_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_composite_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k_composite_bwd<<<grid_for_warps(n_rays), kWarpsPerBlock * 32, smem, stream>>>(
+      sigma, sigma_stride, rgb, rgb_stride, z, dirs, dir_stride, noise, noise_std, background, activation, n_rays,
+      n_samples, g_rgb, g_depth, g_opacity, g_weights, d_sigma, d_sigma_stride, d_rgb, d_rgb_stride);
+  return check_launch();
+}
+
+int mcf_sample_pdf(const float* bins, int bins_stride, int bins_are_z, const float* weights, int w_stride,
+                   const float* cdf_in, int cdf_stride, const float* u, int u_stride, float eps, int n_rays, int n_bins,
+                   int n_importance, const float* z_coarse, int zc_stride, int n_coarse, float* samples, int* inds_out,
+                   float* cdf_out, float* z_merged, cudaStream_t stream) {
+  if (n_rays <= 0 || n_importance <= 0) return 0;
+  if (n_bins < 1 || !u || (!weights && !cdf_in)) return MCF_ERR_BAD_ARG;
+  int npow2 = 0;
+  if (z_merged) {
+    if (!z_coarse) return MCF_ERR_BAD_ARG;
+    npow2 = 1;
+    while (npow2 < n_coarse + n_importance) npow2 <<= 1;
+  }
+  size_t smem = (size_t)kWarpsPerBlock * (2 * (n_bins + 1) + npow2) * sizeof(float);
+  if (smem > 200 * 1024) return MCF_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_sample_pdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k_sample_pdf<<<grid_for_warps(n_rays), kWarpsPerBlock * 32, smem, stream>>>(
+      bins, bins_stride, bins_are_z, weights, w_stride, cdf_in, cdf_stride, u, u_stride, eps, n_rays, n_bins,
+      n_importance, z_coarse, zc_stride, n_coarse, npow2, samples, inds_out, cdf_out, z_merged);
+  return check_launch();
+}
+
+int mcf_masked_l1_fwd(const float* a, const float* b, const float* alphas, float thresh, long long n_points,
+                      float* resid, double* stats, float* mean_out, cudaStream_t stream) {
+  if (n_points <= 0) return 0;
+  if (stats) {
+    cudaError_t e = cudaMemsetAsync(stats, 0, 3 * sizeof(double), stream);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k_masked_l1_fwd<<<(unsigned)((n_points + 255) / 256), 256, 0, stream>>>(a, b, alphas, thresh, n_points, resid, stats);
+  if (stats && mean_out) k_masked_l1_finalize<<<1, 32, 0, stream>>>(stats, n_points, mean_out);
+  return check_launch();
+}
+
+int mcf_masked_l1_bwd(const float* a, const float* b, const float* alphas, float thresh, long long n_points,
+                      const float* g_resid, const float* g_mean, const double* stats, float* d_b, cudaStream_t stream) {
+  if (n_points <= 0) return 0;
+  if (!g_resid && !(g_mean && stats)) return MCF_ERR_BAD_ARG;
+  k_masked_l1_bwd<<<(unsigned)((n_points + 255) / 256), 256, 0, stream>>>(a, b, alphas, thresh, n_points, g_resid,
+                                                                         g_mean, stats, d_b);
+  return check_launch();
+}
+
+}  // extern "C"

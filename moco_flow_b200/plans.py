@@ -1,0 +1,221 @@
+"""Layer programs ("plans") for the tcgen05 chain kernel.
+
+A plan is three small tables (see include/moco_flow_b200.h):
+  * pack   -- how to turn the fp32 nn.Linear tensors into bf16 128B-swizzled weight chunk images
+              (one image = the B operand of up to four K=16 MMAs) and fp32 constants,
+  * chunks -- the order in which the kernel streams those images and which accumulator columns
+              and A-operand block each one feeds,
+  * rounds -- groups of chunks followed by one epilogue (bias/activation/head).
+Plans depend only on the module shapes, so they are built once per module and cached.
+
+Shapes follow models/nerf.py:28-59 and models/nof.py:40-53 of the reference.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+BLK = L.BLOCK_BYTES
+
+
+def _ceil(a: int, b: int) -> int:
+    return (a + b - 1) // b
+
+
+@dataclass
+class Plan:
+    width: int
+    tensor_names: List[str]
+    pack: np.ndarray
+    chunks: np.ndarray
+    rounds: np.ndarray
+    wpack_bytes: int
+    n_consts: int
+    save_tile_bytes: int = 0
+    mask_tile_words: int = 0
+    offsets: Dict[str, int] = field(default_factory=dict)   # named save / mask / const offsets
+    n_raybias: int = 0
+
+
+class _Builder:
+    def __init__(self, width: int):
+        self.width = width
+        self.names: List[str] = []
+        self.pack: List[tuple] = []
+        self.chunks: List[tuple] = []
+        self.rounds: List[tuple] = []
+        self.wbytes = 0
+        self.nconst = 0
+        self.save_bytes = 0
+        self.mask_words = 0
+        self.offsets: Dict[str, int] = {}
+
+    def tensor(self, name: str) -> int:
+        if name not in self.names:
+            self.names.append(name)
+        return self.names.index(name)
+
+    def const(self, name: str, row0: int, nrows: int, col0: int, ncols: int, ld: int, pad_to: Optional[int] = None) -> int:
+        """Copies src[row0:row0+nrows, col0:col0+ncols] (row-major, tightly) into consts; returns float offset."""
+        n = nrows * ncols
+        total = _ceil(max(n, pad_to or 0), 4) * 4
+        off = self.nconst
+        self.pack.append((off, total, 1, self.tensor(name), row0, nrows, col0, ncols, ld, 0))
+        # kind 1 walks i -> (r = i / ncols, c = i % ncols); entries past nrows are zero-filled
+        self.nconst += total
+        return off
+
+    def image(self, name: str, row0: int, nrows: int, col0: int, ncols: int, ld: int, transposed: bool,
+              rows_padded: int) -> tuple:
+        assert ncols <= 64 and nrows <= rows_padded and rows_padded % 8 == 0
+        off, nbytes = self.wbytes, rows_padded * 128
+        self.pack.append((off, nbytes, 0, self.tensor(name), row0, nrows, col0, ncols, ld, int(transposed)))
+        self.wbytes += nbytes
+        return off, nbytes
+
+    def chunk(self, img: tuple, a_buf: int, a_kblock: int, ksteps: int, n: int, acc_col: int, init: bool) -> None:
+        assert 1 <= ksteps <= 4 and n % 16 == 0 and 16 <= n <= 256
+        self.chunks.append((img[0], img[1], a_buf, a_kblock, ksteps, 1 if init else 0, n, acc_col))
+
+    def round(self, epi: int, n_out: int, acc_col: int, chunk_begin: int, raybias: int = -1, const_off: int = 0,
+              aux_off: int = 0, save_off: int = L.NONE, mask_off: int = L.NONE) -> None:
+        self.rounds.append((epi, n_out, acc_col, chunk_begin, len(self.chunks), raybias, const_off, aux_off,
+                            save_off, mask_off, 0))
+
+    def save_slot(self, key: str, n_blocks: int) -> int:
+        off = self.save_bytes
+        self.offsets["save_" + key] = off
+        self.save_bytes += n_blocks * BLK
+        return off
+
+    def mask_slot(self, key: str, n_cols: int) -> int:
+        off = self.mask_words
+        self.offsets["mask_" + key] = off
+        self.mask_words += _ceil(n_cols, 32) * 128
+        return off
+
+    def finish(self, n_raybias: int = 0) -> Plan:
+        assert len(self.chunks) <= 128 and len(self.rounds) <= 24 and len(self.names) <= 32, \
+            (len(self.chunks), len(self.rounds), len(self.names))
+        return Plan(self.width, list(self.names),
+                    np.array(self.pack, dtype=L.PACK_DT), np.array(self.chunks, dtype=L.CHUNK_DT),
+                    np.array(self.rounds, dtype=L.ROUND_DT), self.wbytes, max(self.nconst, 4),
+                    self.save_bytes, self.mask_words, dict(self.offsets), n_raybias)
+
+
+def _check_common(W: int, cx: int) -> None:
+    if W not in (128, 256):
+        raise ValueError(f"fused MLP kernels support hidden width 128 or 256, got {W}")
+    if cx > 64:
+        raise ValueError(f"fused MLP kernels support in_channels_xyz <= 64, got {cx}")
+
+
+def _trunk_sources(i: int, skips: Sequence[int], cx: int, nkb: int, skip_extra: int):
+    """[(a_buf, a_kblock, ksteps, weight col0, ncols)] of trunk layer i (0-based)."""
+    kx = _ceil(cx, 16)
+    if i == 0:
+        return [(0, 0, kx, 0, cx)]
+    src = []
+    base = 0
+    if i in skips:
+        src.append((0, 0, kx, 0, cx))
+        base = cx + skip_extra
+    src += [(1, kb, 4, base + 64 * kb, 64) for kb in range(nkb)]
+    return src
+
+
+def nerf_forward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: int, sigma_only: bool,
+                      training: bool) -> Plan:
+    """models/nerf.py:61-102 as a chain program."""
+    _check_common(W, cx)
+    b = _Builder(W)
+    nkb, NH = W // 64, W // 128
+    if training:
+        b.save_slot("x0", 1)
+        b.save_slot("extra", 1)
+    for i in range(D):
+        wname, bname = f"xyz_encoding_{i+1}.0.weight", f"xyz_encoding_{i+1}.0.bias"
+        ld = cx if i == 0 else (W + cx if i in skips else W)
+        c0 = len(b.chunks)
+        for si, (abuf, kb, ks, col0, ncols) in enumerate(_trunk_sources(i, skips, cx, nkb, 0)):
+            for nh in range(NH):
+                img = b.image(wname, nh * 128, 128, col0, ncols, ld, False, 128)
+                b.chunk(img, abuf, kb, ks, 128, nh * 128, init=(si == 0))
+        boff = b.const(bname, 0, 1, 0, W, W)
+        last = i == D - 1
+        aux = 0
+        if last:
+            aux = b.const("sigma.weight", 0, 1, 0, W, W)
+            b.const("sigma.bias", 0, 1, 0, 1, 1)  # lands at aux + W
+        save = b.save_slot(f"h{i+1}", nkb) if training else L.NONE
+        mask = b.mask_slot(f"h{i+1}", W) if training else L.NONE
+        b.round(L.EPI_RELU_SIGMA if last else L.EPI_RELU, W, 0, c0, const_off=boff, aux_off=aux, save_off=save,
+                mask_off=mask)
+    if not sigma_only:
+        c0 = len(b.chunks)
+        for kb in range(nkb):
+            for nh in range(NH):
+                img = b.image("xyz_encoding_final.weight", nh * 128, 128, 64 * kb, 64, W, False, 128)
+                b.chunk(img, 1, kb, 4, 128, nh * 128, init=(kb == 0))
+        boff = b.const("xyz_encoding_final.bias", 0, 1, 0, W, W)
+        b.round(L.EPI_LINEAR, W, 0, c0, const_off=boff, save_off=b.save_slot("feat", nkb) if training else L.NONE)
+        half = W // 2
+        c0 = len(b.chunks)
+        for kb in range(nkb):
+            img = b.image("extra_encoding.0.weight", 0, half, 64 * kb, 64, W + extra_dim, False, half)
+            b.chunk(img, 1, kb, 4, half, 0, init=(kb == 0))
+        boff = b.const("extra_encoding.0.bias", 0, 1, 0, half, half)
+        aux = b.const("rgb.0.weight", 0, 3, 0, half, half)
+        b.const("rgb.0.bias", 0, 1, 0, 3, 3)  # lands at aux + 3*half
+        b.round(L.EPI_NERF_RGB, half, 0, c0, raybias=(0 if extra_dim > 0 else -1), const_off=boff, aux_off=aux,
+                save_off=b.save_slot("he", _ceil(half, 64)) if training else L.NONE,
+                mask_off=b.mask_slot("he", half) if training else L.NONE)
+    return b.finish(n_raybias=1 if (extra_dim > 0 and not sigma_only) else 0)
+
+
+def nof_forward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: int, use_quat: bool,
+                     training: bool) -> Plan:
+    """models/nof.py:55-85 as a chain program.  The per-ray index-embedding columns of layer 1 and of
+    the skip layers are folded into per-ray bias vectors (mcf_ray_bias), in list order."""
+    _check_common(W, cx)
+    b = _Builder(W)
+    nkb, NH = W // 64, W // 128
+    if training:
+        b.save_slot("x0", 1)
+        b.save_slot("extra", 1)
+    rb = 0
+    for i in range(D):
+        wname, bname = f"nof_encoding_{i+1}.0.weight", f"nof_encoding_{i+1}.0.bias"
+        cin = cx + extra_dim
+        ld = cin if i == 0 else (W + cin if i in skips else W)
+        c0 = len(b.chunks)
+        for si, (abuf, kb, ks, col0, ncols) in enumerate(_trunk_sources(i, skips, cx, nkb, extra_dim)):
+            for nh in range(NH):
+                img = b.image(wname, nh * 128, 128, col0, ncols, ld, False, 128)
+                b.chunk(img, abuf, kb, ks, 128, nh * 128, init=(si == 0))
+        folded = (i == 0 or i in skips) and extra_dim > 0
+        boff = 0 if folded else b.const(bname, 0, 1, 0, W, W)
+        save = b.save_slot(f"h{i+1}", nkb) if training else L.NONE
+        mask = b.mask_slot(f"h{i+1}", W) if training else L.NONE
+        b.round(L.EPI_RELU, W, 0, c0, raybias=(rb if folded else -1), const_off=boff, save_off=save, mask_off=mask)
+        if folded:
+            rb += 1
+    n_head = 9 if use_quat else 3
+    c0 = len(b.chunks)
+    for kb in range(nkb):
+        img = b.image("nof_encoding_final.weight", 0, n_head, 64 * kb, 64, W, False, 16)
+        b.chunk(img, 1, kb, 4, 16, 0, init=(kb == 0))
+    boff = b.const("nof_encoding_final.bias", 0, 1, 0, n_head, n_head, pad_to=16)
+    b.round(L.EPI_NOF_HEAD, 16, 0, c0, const_off=boff)
+    if rb > 4:
+        raise ValueError("at most 4 folded layers (first + 3 skips) are supported")
+    return b.finish(n_raybias=rb)
+
+
+def folded_layers(D: int, skips: Sequence[int]) -> List[int]:
+    """0-based trunk layers of a NoF whose extra-feature columns are folded, in raybias order."""
+    return [i for i in range(D) if i == 0 or i in skips]

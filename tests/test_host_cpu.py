@@ -1,0 +1,131 @@
+"""CPU-only checks of the host logic: library exports, struct layouts, plans, image helpers."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import moco_flow_b200 as mf
+from moco_flow_b200 import _lib as L
+from moco_flow_b200 import plans as P
+from tests.helpers import from_images, to_images
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from moco_flow_b200.build import build
+    path = build()
+    header = open(os.path.join(ROOT, "include", "moco_flow_b200.h")).read()
+    declared = set(re.findall(r"\bint\s+(mcf_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    lib = C.CDLL(path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mcf_abi_version() == 1
+
+
+def test_struct_layouts_match_header(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\n'
+                   'int main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(mcf_chain_params_t), '
+                   'sizeof(mcf_dw_params_t), sizeof(mcf_chunk_t), sizeof(mcf_round_t), sizeof(mcf_pack_t), '
+                   'offsetof(mcf_chain_params_t, d_xyz), offsetof(mcf_dw_params_t, n_tiles));return 0;}\n'
+                   % os.path.join(ROOT, "include", "moco_flow_b200.h"))
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(L.ChainParams), C.sizeof(L.DwParams), L.CHUNK_DT.itemsize, L.ROUND_DT.itemsize,
+            L.PACK_DT.itemsize, L.ChainParams.d_xyz.offset, L.DwParams.n_tiles.offset]
+    assert got == want
+
+
+def test_image_helpers_roundtrip():
+    x = torch.randn(300, 100)
+    img = to_images(x)
+    assert img.shape == (3, 2, 128, 8, 8)
+    back = from_images(img, 300, 100)
+    assert torch.equal(back, x.to(torch.bfloat16).float())
+    # row r chunk c lives at chunk c ^ (r & 7)
+    x2 = torch.zeros(128, 64)
+    x2[5, 8:16] = 1.0
+    assert (to_images(x2)[0, 0, 5, 1 ^ 5, :] == 0x3F80).all()
+
+
+def test_nerf_plan_shapes():
+    pl = P.nerf_forward_plan(8, 256, 63, (4,), 5, sigma_only=False, training=False)
+    assert len(pl.chunks) == 72 and pl.wpack_bytes == 72 * 16384
+    assert len(pl.rounds) == 10
+    assert [int(r["epi"]) for r in pl.rounds] == [0] * 7 + [1, 2, 3]
+    assert int(pl.rounds[4]["chunk_end"] - pl.rounds[4]["chunk_begin"]) == 10  # skip layer: x0 + 4 h blocks, 2 halves
+    so = P.nerf_forward_plan(8, 256, 63, (4,), 5, sigma_only=True, training=False)
+    assert len(so.rounds) == 8 and len(so.chunks) == 60
+    tr = P.nerf_forward_plan(8, 256, 63, (4,), 5, sigma_only=False, training=True)
+    assert tr.save_tile_bytes == (1 + 1 + 8 * 4 + 4 + 2) * 16384
+    assert tr.mask_tile_words == 8 * 8 * 128 + 4 * 128
+    # every chunk consumes columns that exist; first chunk of each accumulator region initialises it
+    for r in pl.rounds:
+        seen = set()
+        for c in pl.chunks[int(r["chunk_begin"]):int(r["chunk_end"])]:
+            key = int(c["acc_col"])
+            assert bool(c["flags"] & 1) == (key not in seen)
+            seen.add(key)
+
+
+def test_nof_plan_shapes():
+    pl = P.nof_forward_plan(4, 128, 33, (2,), 33, True, training=False)
+    assert len(pl.rounds) == 5 and pl.n_raybias == 2
+    assert [int(r["raybias"]) for r in pl.rounds] == [0, -1, 1, -1, -1]
+    assert int(pl.chunks[0]["ksteps"]) == 3  # 33 channels -> K = 48
+    assert int(pl.rounds[-1]["epi"]) == L.EPI_NOF_HEAD
+
+
+def test_unsupported_shapes_fail_loudly():
+    with pytest.raises(ValueError):
+        P.nerf_forward_plan(8, 192, 63, (4,), 5, False, False)
+    with pytest.raises(ValueError):
+        P.nerf_forward_plan(8, 256, 93, (4,), 5, False, False)
+
+
+def test_modules_keep_reference_state_dict_names():
+    from oracle import moco_oracle as orc
+    n = mf.NeRF(8, 256, 63, [4], "ind", 5)
+    assert {k: tuple(v.shape) for k, v in n.state_dict().items()} == \
+        {k: tuple(v.shape) for k, v in orc.make_nerf_params(orc.C2F_NERF, 0).items()}
+    f = mf.NoF(4, 128, 33, [2], "ind", 33, True)
+    assert {k: tuple(v.shape) for k, v in f.state_dict().items()} == \
+        {k: tuple(v.shape) for k, v in orc.make_nof_params(orc.C2F_NOF, 0).items()}
+    e = mf.Embedding(3, 10)
+    assert e.out_channels == 63 and e.weights == [1] * 10
+    e.set_weights(0)
+    assert e.weights == [0] * 10
+    with pytest.raises(AssertionError):
+        e.set_weights([1.0, 2.0])
+    assert torch.equal(e.freq_bands, 2 ** torch.linspace(0, 9, 10))
+    assert torch.equal(mf.Embedding(3, 4, logscale=False).freq_bands, torch.linspace(1, 8, 4))
+
+
+def test_factories_and_errors():
+    m = mf.get_model(dict(type="NoF", D=4, W=128, in_channels_xyz=33, skips=[2], extra_feat_type="ind",
+                          extra_feat_dim=33, use_quat=True))
+    assert isinstance(m, mf.NoF)
+    assert isinstance(mf.get_loss(dict(type="MSE")), mf.MSELoss)
+    with pytest.raises(ValueError):
+        mf.get_model(dict(type="Foo"))
+    with pytest.raises(ValueError):
+        mf.get_loss(dict(type="Foo"))
+    with pytest.raises(AssertionError):
+        mf.NeRF(extra_feat_type="bogus")
+    with pytest.raises(AssertionError):
+        mf.NoF(extra_feat_type="none")
+
+
+def test_no_cpu_fallback():
+    n = mf.NeRF(8, 256, 63, [4], "ind", 5)
+    with pytest.raises(RuntimeError):
+        n(torch.zeros(4, 68))
+    with pytest.raises(RuntimeError):
+        mf.Embedding(3, 2)(torch.zeros(4, 3))
