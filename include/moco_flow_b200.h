@@ -191,7 +191,13 @@ typedef struct {
   long long fwd_mask_tile_words;
   uint32_t fwd_x0_off, fwd_he_off;
   float* d_xyz;            /* [M][3] grad w.r.t. the input points, or NULL   */
-  float* d_head;           /* NeRF: [M][4] {d_pre_rgb(3), d_sigma}; NoF: unused */
+  float* d_head;           /* fp32 head gradients: NeRF [M][4] {d_pre_rgb(3), d_sigma}; NoF [M][12] {d v,s,t} */
+  /* per-ray features stored as a bf16 image block next to the saved operands (training forward), so
+   * that the weight-gradient GEMM sees the folded input columns */
+  const float* rayfeat;    /* [n_rays][rayfeat_stride]                       */
+  int32_t rayfeat_stride, rayfeat_dim;
+  uint32_t extra_save_off; /* 0xFFFFFFFF none                                */
+  uint32_t dhead_save_off; /* backward: image block of the head gradients    */
   int32_t max_ctas;        /* 0 = one CTA per SM                             */
 } mcf_chain_params_t;
 
@@ -210,6 +216,21 @@ typedef struct {
   int32_t max_ctas;
 } mcf_dw_params_t;
 int mcf_dw_gemm(const mcf_dw_params_t* params_host, cudaStream_t stream);
+
+/* Scatter the staging results of mcf_dw_gemm into the parameter-gradient buffer:
+ * dst[dst_off + r*dst_ld + c] = transposed ? src[src_off + c*src_ld + r] : src[src_off + r*src_ld + c]. */
+typedef struct {
+  uint32_t src_off, dst_off;
+  int32_t src_ld, dst_ld;
+  int32_t nrows, ncols;
+  int32_t transposed;
+  int32_t reserved;
+} mcf_unpack_t;
+int mcf_unpack(const mcf_unpack_t* table_dev, int n_entries, const float* staging, float* grads,
+               cudaStream_t stream);
+
+/* out[c] += sum_m src[m*stride + c], c < ncols (<= 16): bias gradients of the heads */
+int mcf_colsum(const float* src, long long n_rows, int stride, int ncols, float* out, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,9 @@ ROUND_DT = np.dtype([("epi", "<u2"), ("n_out", "<u2"), ("acc_col", "<u2"), ("chu
                      ("save_off", "<u4"), ("mask_off", "<u4"), ("reserved", "<u4")])
 PACK_DT = np.dtype([("dst_off", "<u4"), ("bytes", "<u4"), ("kind", "<i4"), ("tensor", "<i4"), ("row0", "<i4"),
                     ("nrows", "<i4"), ("col0", "<i4"), ("ncols", "<i4"), ("ld", "<i4"), ("transposed", "<i4")])
-assert CHUNK_DT.itemsize == 16 and ROUND_DT.itemsize == 32 and PACK_DT.itemsize == 40
+UNPACK_DT = np.dtype([("src_off", "<u4"), ("dst_off", "<u4"), ("src_ld", "<i4"), ("dst_ld", "<i4"), ("nrows", "<i4"),
+                      ("ncols", "<i4"), ("transposed", "<i4"), ("reserved", "<i4")])
+assert CHUNK_DT.itemsize == 16 and ROUND_DT.itemsize == 32 and PACK_DT.itemsize == 40 and UNPACK_DT.itemsize == 32
 
 _vp, _i32, _i64, _u32, _f32 = C.c_void_p, C.c_int32, C.c_longlong, C.c_uint32, C.c_float
 
@@ -47,7 +49,8 @@ class ChainParams(C.Structure):
         ("save", _vp), ("save_tile_bytes", _i64), ("masks", _vp), ("mask_tile_words", _i64), ("x0_save_off", _u32),
         ("g_out", _vp), ("fwd_out", _vp), ("fwd_save", _vp), ("fwd_save_tile_bytes", _i64), ("fwd_masks", _vp),
         ("fwd_mask_tile_words", _i64), ("fwd_x0_off", _u32), ("fwd_he_off", _u32),
-        ("d_xyz", _vp), ("d_head", _vp), ("max_ctas", _i32),
+        ("d_xyz", _vp), ("d_head", _vp), ("rayfeat", _vp), ("rayfeat_stride", _i32), ("rayfeat_dim", _i32),
+        ("extra_save_off", _u32), ("dhead_save_off", _u32), ("max_ctas", _i32),
     ]
 
 
@@ -63,7 +66,7 @@ class DwParams(C.Structure):
 EXPORTS = [
     "mcf_abi_version", "mcf_device_error_flag", "mcf_coarse_samples", "mcf_ray_points", "mcf_pe_fwd", "mcf_pe_bwd",
     "mcf_ray_bias", "mcf_composite_fwd", "mcf_composite_bwd", "mcf_sample_pdf", "mcf_masked_l1_fwd",
-    "mcf_masked_l1_bwd", "mcf_pack", "mcf_chain_launch", "mcf_dw_gemm",
+    "mcf_masked_l1_bwd", "mcf_pack", "mcf_chain_launch", "mcf_dw_gemm", "mcf_unpack", "mcf_colsum",
 ]
 
 _lib = None

@@ -1,0 +1,284 @@
+"""Autograd wiring of the fused chains: training forward (saves bf16 operand images + ReLU bit masks),
+backward dX chain, weight-gradient GEMMs and the scatter into per-parameter gradients.
+
+Gradient flow follows the reference's autograd graph: parameters of the module and
+the input points ``xyz`` (when they come out of a NoF); never the per-ray features or the rays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from . import plans as P
+from .mlp import fold_bias, setup_input
+
+
+def _n_tiles(M: int) -> int:
+    return (M + L.TILE_ROWS - 1) // L.TILE_ROWS
+
+
+def _dev_table(arr: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(device)
+
+
+class _TrainState:
+    """Cached per-module backward programs (dX plan with/without input gradient, grad job tables)."""
+
+    def __init__(self):
+        self.bwd: Dict[bool, ops.PackedPlan] = {}
+        self.grad: Dict[bool, P.GradPlan] = {}
+        self.unpack_dev: Dict[bool, torch.Tensor] = {}
+
+
+def _train_state(model) -> _TrainState:
+    st = model.__dict__.get("_mcf_train")
+    if st is None or model.__dict__.get("_mcf_plans") is None:
+        st = _TrainState()
+        model.__dict__["_mcf_train"] = st
+    return st
+
+
+def _run_grad_plan(gp: P.GradPlan, unpack_dev: torch.Tensor, fwd_save: torch.Tensor, fwd_tile_bytes: int,
+                   bwd_save: torch.Tensor, bwd_tile_bytes: int, n_tiles: int, d_head: torch.Tensor,
+                   wanted: set) -> torch.Tensor:
+    dev = fwd_save.device
+    staging = torch.zeros(gp.staging_floats, device=dev)
+    grads = torch.zeros(gp.total_floats, device=dev)
+    src = {"fwd": (fwd_save, fwd_tile_bytes), "bwd": (bwd_save, bwd_tile_bytes)}
+    for j in gp.jobs:
+        if not any(n in wanted for n in j.params):
+            continue
+        pb, pt = src[j.p_src]
+        qb, qt = src[j.q_src]
+        out = staging[j.st_off:j.st_off + j.n_i * j.ld].view(j.n_i, j.ld)
+        cs = staging[j.colsum_off:j.colsum_off + j.n_i] if j.colsum_off >= 0 else None
+        ops.dw_gemm(pb, pt, j.p_off, j.p_cols, qb, qt, j.q_off, j.q_cols, out, j.n_i, j.n_j, n_tiles, cs)
+    ncols, stride, hc = gp.head_colsum
+    L.check(L.lib().mcf_colsum(L.ptr(d_head), C.c_longlong(d_head.shape[0]), C.c_int(stride), C.c_int(ncols),
+                               C.c_void_p(staging.data_ptr() + 4 * hc), L.stream_ptr()), "mcf_colsum")
+    L.check(L.lib().mcf_unpack(L.ptr(unpack_dev), C.c_int(len(gp.unpack)), L.ptr(staging), L.ptr(grads),
+                               L.stream_ptr()), "mcf_unpack")
+    return grads
+
+
+def _param_grads(gp: P.GradPlan, flat: torch.Tensor, names: List[str], needs: List[bool]):
+    out = []
+    for n, need in zip(names, needs):
+        if not need:
+            out.append(None)
+            continue
+        shp = gp.param_shapes[n]
+        off = gp.param_offsets[n]
+        out.append(flat[off:off + int(np.prod(shp))].view(shp))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# NeRF
+# ------------------------------------------------------------------------------------------------
+class _NeRFFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, pe, rows_per_ray, xyz, dense, ray_feat, names, *params):
+        from .autograd_mlp import _rows
+        M = _rows(xyz, dense)
+        R = M // rows_per_ray
+        dev = (dense if dense is not None else xyz).device
+        pp = model._plan(False, True)
+        plan = pp.plan
+        cp = ops.chain_params(pp, M, rows_per_ray, R)
+        xyz_c = None if xyz is None else xyz.detach().contiguous()
+        keep = setup_input(cp, xyz_c, pe, None if dense is None else dense.detach(), model.in_channels_xyz)
+        E = model._extra_dim()
+        rf = None
+        if E > 0:
+            lin = model.extra_encoding[0]
+            rf = ray_feat[:, :E].detach()
+            if rf.stride(-1) != 1:
+                rf = rf.contiguous()
+            rb = fold_bias(lin.weight, model.W, lin.bias, rf)
+            cp.raybias[0] = rb.data_ptr()
+            cp.rayfeat, cp.rayfeat_stride, cp.rayfeat_dim = rf.data_ptr(), rf.stride(0), rf.shape[1]
+            cp.extra_save_off = plan.offsets["save_extra"]
+            keep += [rb, rf]
+        nt = _n_tiles(M)
+        save = torch.empty(nt * plan.save_tile_bytes, dtype=torch.uint8, device=dev)
+        masks = torch.empty(nt * plan.mask_tile_words, dtype=torch.int32, device=dev)
+        out = torch.empty(M, 4, device=dev)
+        cp.out, cp.out_stride, cp.sigma_col = out.data_ptr(), 4, 3
+        cp.save, cp.save_tile_bytes = save.data_ptr(), plan.save_tile_bytes
+        cp.masks, cp.mask_tile_words = masks.data_ptr(), plan.mask_tile_words
+        cp.x0_save_off = plan.offsets["save_x0"]
+        ops.launch_chain(cp)
+        ctx.model, ctx.pe, ctx.names, ctx.M, ctx.S = model, pe, names, M, rows_per_ray
+        ctx.dense_mode = dense is not None
+        ctx.need_dx = xyz is not None and xyz.requires_grad
+        ctx.save_for_backward(save, masks, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        model, M = ctx.model, ctx.M
+        save, masks, out = ctx.saved_tensors
+        dev = out.device
+        st = _train_state(model)
+        fwd_plan = model._plan(False, True).plan
+        need_dx = bool(ctx.need_dx)
+        if need_dx not in st.bwd:
+            bplan = P.nerf_backward_plan(model.D, model.W, model.in_channels_xyz, tuple(model.skips),
+                                         model._extra_dim(), need_dx, fwd_plan)
+            st.bwd[need_dx] = ops.PackedPlan(bplan, dev)
+            shapes = {k: tuple(v.shape) for k, v in model.named_parameters()}
+            st.grad[need_dx] = P.nerf_grad_plan(model.D, model.W, model.in_channels_xyz, tuple(model.skips),
+                                                model._extra_dim(), shapes, fwd_plan, bplan)
+            st.unpack_dev[need_dx] = _dev_table(st.grad[need_dx].unpack, dev)
+        bpp = st.bwd[need_dx]
+        bpp.repack(model._param_dict())
+        bplan = bpp.plan
+        nt = _n_tiles(M)
+        cp = ops.chain_params(bpp, M, ctx.S, M // ctx.S)
+        cp.prologue = L.PRO_B_NERF
+        g_out = g_out.contiguous()
+        cp.g_out, cp.fwd_out = g_out.data_ptr(), out.data_ptr()
+        cp.fwd_save, cp.fwd_save_tile_bytes = save.data_ptr(), fwd_plan.save_tile_bytes
+        cp.fwd_masks, cp.fwd_mask_tile_words = masks.data_ptr(), fwd_plan.mask_tile_words
+        cp.fwd_x0_off = fwd_plan.offsets["save_x0"]
+        bsave = torch.empty(nt * bplan.save_tile_bytes, dtype=torch.uint8, device=dev)
+        cp.save, cp.save_tile_bytes = bsave.data_ptr(), bplan.save_tile_bytes
+        cp.x0_save_off = bplan.offsets["save_dye"]
+        cp.dhead_save_off = bplan.offsets["save_dhead"]
+        d_head = torch.empty(M, 4, device=dev)
+        cp.d_head = d_head.data_ptr()
+        d_xyz = None
+        if need_dx:
+            d_xyz = torch.empty(M, 3, device=dev)
+            cp.d_xyz = d_xyz.data_ptr()
+            ops.set_pe(cp, ctx.pe.frequencies(), ctx.pe.multipliers(), model.in_channels_xyz)
+        ops.launch_chain(cp)
+        needs = list(ctx.needs_input_grad[7:])
+        wanted = {n for n, need in zip(ctx.names, needs) if need}
+        pgrads = [None] * len(ctx.names)
+        if wanted:
+            gp = st.grad[need_dx]
+            flat = _run_grad_plan(gp, st.unpack_dev[need_dx], save, fwd_plan.save_tile_bytes, bsave,
+                                  bplan.save_tile_bytes, nt, d_head, wanted)
+            pgrads = _param_grads(gp, flat, ctx.names, needs)
+        return (None, None, None, d_xyz, None, None, None, *pgrads)
+
+
+def nerf_autograd(model, xyz, pe, dense, ray_feat, rows_per_ray, sigma_only):
+    if sigma_only:
+        raise NotImplementedError("differentiating the sigma-only evaluation is not part of the render path")
+    if dense is not None and dense.requires_grad:
+        raise NotImplementedError("gradients w.r.t. pre-embedded inputs are not provided; pass xyz + Embedding")
+    names = [n for n, _ in model.named_parameters()]
+    params = [p for _, p in model.named_parameters()]
+    return _NeRFFn.apply(model, pe, rows_per_ray, xyz, dense, ray_feat, names, *params)
+
+
+# ------------------------------------------------------------------------------------------------
+# NoF
+# ------------------------------------------------------------------------------------------------
+class _NoFFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, pe, rows_per_ray, xyz, dense, ray_feat, names, *params):
+        M = int(xyz.shape[0])
+        R = M // rows_per_ray
+        dev = xyz.device
+        pp = model._plan(True)
+        plan = pp.plan
+        cp = ops.chain_params(pp, M, rows_per_ray, R)
+        xyz_c = xyz.detach().contiguous()
+        keep = setup_input(cp, xyz_c, pe, None if dense is None else dense.detach(), model.in_channels_xyz)
+        E, cx = model.extra_feat_dim, model.in_channels_xyz
+        if E > 0:
+            rf = ray_feat[:, :E].detach()
+            if rf.stride(-1) != 1:
+                rf = rf.contiguous()
+            for k, i in enumerate(P.folded_layers(model.D, tuple(model.skips))):
+                lin = getattr(model, f"nof_encoding_{i+1}")[0]
+                rb = fold_bias(lin.weight, cx, lin.bias, rf)
+                cp.raybias[k] = rb.data_ptr()
+                keep.append(rb)
+            cp.rayfeat, cp.rayfeat_stride, cp.rayfeat_dim = rf.data_ptr(), rf.stride(0), rf.shape[1]
+            cp.extra_save_off = plan.offsets["save_extra"]
+            keep.append(rf)
+        nt = _n_tiles(M)
+        # the per-ray feature block must exist (zeros) even when E == 0, because the layer-1 weight GEMM reads it
+        save = (torch.empty if E > 0 else torch.zeros)(nt * plan.save_tile_bytes, dtype=torch.uint8, device=dev)
+        masks = torch.empty(nt * plan.mask_tile_words, dtype=torch.int32, device=dev)
+        out = torch.empty(M, 3, device=dev)
+        head_save = torch.empty(M, 12, device=dev)
+        cp.out, cp.out_stride, cp.use_quat = out.data_ptr(), 3, int(model.use_quat)
+        cp.head_save = head_save.data_ptr()
+        cp.save, cp.save_tile_bytes = save.data_ptr(), plan.save_tile_bytes
+        cp.masks, cp.mask_tile_words = masks.data_ptr(), plan.mask_tile_words
+        cp.x0_save_off = plan.offsets["save_x0"]
+        ops.launch_chain(cp)
+        ctx.model, ctx.pe, ctx.names, ctx.M, ctx.S = model, pe, names, M, rows_per_ray
+        ctx.need_dx = xyz.requires_grad
+        ctx.save_for_backward(save, masks, head_save)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        model, M = ctx.model, ctx.M
+        save, masks, head_save = ctx.saved_tensors
+        dev = save.device
+        st = _train_state(model)
+        fwd_plan = model._plan(True).plan
+        need_dx = bool(ctx.need_dx)
+        if need_dx not in st.bwd:
+            bplan = P.nof_backward_plan(model.D, model.W, model.in_channels_xyz, tuple(model.skips),
+                                        model.extra_feat_dim, bool(model.use_quat), need_dx, fwd_plan)
+            st.bwd[need_dx] = ops.PackedPlan(bplan, dev)
+            shapes = {k: tuple(v.shape) for k, v in model.named_parameters()}
+            st.grad[need_dx] = P.nof_grad_plan(model.D, model.W, model.in_channels_xyz, tuple(model.skips),
+                                               model.extra_feat_dim, bool(model.use_quat), shapes, fwd_plan, bplan)
+            st.unpack_dev[need_dx] = _dev_table(st.grad[need_dx].unpack, dev)
+        bpp = st.bwd[need_dx]
+        bpp.repack(model._param_dict())
+        bplan = bpp.plan
+        nt = _n_tiles(M)
+        cp = ops.chain_params(bpp, M, ctx.S, M // ctx.S)
+        cp.prologue = L.PRO_B_NOF
+        cp.use_quat = int(model.use_quat)
+        g_out = g_out.contiguous()
+        cp.g_out, cp.head_save = g_out.data_ptr(), head_save.data_ptr()
+        cp.fwd_save, cp.fwd_save_tile_bytes = save.data_ptr(), fwd_plan.save_tile_bytes
+        cp.fwd_masks, cp.fwd_mask_tile_words = masks.data_ptr(), fwd_plan.mask_tile_words
+        cp.fwd_x0_off = fwd_plan.offsets["save_x0"]
+        bsave = torch.empty(nt * bplan.save_tile_bytes, dtype=torch.uint8, device=dev)
+        cp.save, cp.save_tile_bytes = bsave.data_ptr(), bplan.save_tile_bytes
+        cp.x0_save_off = bplan.offsets["save_ghead"]
+        d_head = torch.zeros(M, 12, device=dev)
+        cp.d_head = d_head.data_ptr()
+        d_xyz = None
+        if need_dx:
+            d_xyz = torch.empty(M, 3, device=dev)
+            cp.d_xyz = d_xyz.data_ptr()
+            ops.set_pe(cp, ctx.pe.frequencies(), ctx.pe.multipliers(), model.in_channels_xyz)
+        ops.launch_chain(cp)
+        needs = list(ctx.needs_input_grad[7:])
+        wanted = {n for n, need in zip(ctx.names, needs) if need}
+        pgrads = [None] * len(ctx.names)
+        if wanted:
+            gp = st.grad[need_dx]
+            flat = _run_grad_plan(gp, st.unpack_dev[need_dx], save, fwd_plan.save_tile_bytes, bsave,
+                                  bplan.save_tile_bytes, nt, d_head, wanted)
+            pgrads = _param_grads(gp, flat, ctx.names, needs)
+        return (None, None, None, d_xyz, None, None, None, *pgrads)
+
+
+def nof_autograd(model, xyz, pe, dense, ray_feat, rows_per_ray):
+    if dense is not None and dense.requires_grad:
+        raise NotImplementedError("gradients w.r.t. pre-embedded inputs are not provided; pass xyz + Embedding")
+    if dense is not None and xyz.requires_grad:
+        raise NotImplementedError("input-point gradients need the fused xyz encoder (pass pe=..., not dense=...)")
+    names = [n for n, _ in model.named_parameters()]
+    params = [p for _, p in model.named_parameters()]
+    return _NoFFn.apply(model, pe, rows_per_ray, xyz, dense, ray_feat, names, *params)

@@ -343,6 +343,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         float d0 = g.x * o.x * (1.f - o.x), d1 = g.y * o.y * (1.f - o.y), d2 = g.z * o.z * (1.f - o.z);
         st.sigma = g.w;
         if (valid && p.d_head) *reinterpret_cast<float4*>(p.d_head + m * 4) = make_float4(d0, d1, d2, g.w);
+        if (saving && p.dhead_save_off != kNone) {
+          uint8_t* blk = save_tile + p.dhead_save_off;
+          uint4 v = make_uint4(pack_bf16x2(d0, d1), pack_bf16x2(d2, g.w), 0u, 0u);
+          *reinterpret_cast<uint4*>(blk + sw128_off(row, 0)) = v;
+#pragma unroll
+          for (int c8 = 1; c8 < 8; ++c8) *reinterpret_cast<uint4*>(blk + sw128_off(row, c8)) = make_uint4(0, 0, 0, 0);
+        }
         const mcf_round_t& r0 = tab.rounds[0];
         const int nhe = W / 2;
         const float* wrgb = p.consts + r0.aux_off;  // [3][W/2]
@@ -380,6 +387,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           d16[0] = g[0]; d16[1] = g[1]; d16[2] = g[2];
           st.dx[0] = g[0]; st.dx[1] = g[1]; st.dx[2] = g[2];
         }
+        if (valid && p.d_head) {
+          float4* dh = reinterpret_cast<float4*>(p.d_head + m * 12);
+          dh[0] = make_float4(d16[0], d16[1], d16[2], d16[3]);
+          dh[1] = make_float4(d16[4], d16[5], d16[6], d16[7]);
+          dh[2] = make_float4(d16[8], 0.f, 0.f, 0.f);
+        }
         uint4 v;
         v.x = pack_bf16x2(d16[0], d16[1]); v.y = pack_bf16x2(d16[2], d16[3]);
         v.z = pack_bf16x2(d16[4], d16[5]); v.w = pack_bf16x2(d16[6], d16[7]);
@@ -387,6 +400,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         v.x = pack_bf16x2(d16[8], d16[9]); v.y = pack_bf16x2(d16[10], d16[11]);
         v.z = pack_bf16x2(d16[12], d16[13]); v.w = pack_bf16x2(d16[14], d16[15]);
         store_h8(hbuf, row, 8, v);
+#pragma unroll
+        for (int c8 = 2; c8 < 8; ++c8) store_h8(hbuf, row, c8 * 8, make_uint4(0, 0, 0, 0));
+      }
+      if (saving && p.extra_save_off != kNone && p.rayfeat != nullptr) {
+        // per-ray feature columns as an image block, written straight to the save record
+        const float* rf = p.rayfeat + ray * p.rayfeat_stride;
+        uint8_t* blk = save_tile + p.extra_save_off;
+        for (int c8 = 0; c8 < 8; ++c8) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = c8 * 8 + j;
+            f[j] = (valid && c < p.rayfeat_dim) ? __ldg(rf + c) : 0.f;
+          }
+          uint4 v;
+          v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+          v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(blk + sw128_off(row, c8)) = v;
+        }
       }
       fence_proxy_async_smem();
       if (saving && p.x0_save_off != kNone) {
@@ -509,7 +541,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             }
           }
         } else if (rd.epi == MCF_EPI_B_MASK || rd.epi == MCF_EPI_B_MASK_SIGMA || rd.epi == MCF_EPI_B_LINEAR) {
-          const uint32_t* mk = (rd.mask_off != kNone) ? (p.fwd_masks + tile * p.fwd_mask_tile_words + rd.mask_off) : nullptr;
+          const uint32_t* mk = (rd.epi != MCF_EPI_B_LINEAR && rd.mask_off != kNone)
+                                   ? (p.fwd_masks + tile * p.fwd_mask_tile_words + rd.mask_off) : nullptr;
           for (int c0 = 0; c0 < rd.n_out; c0 += 32) {
             uint32_t v[32];
             float f[32];
@@ -631,9 +664,58 @@ __global__ void k_pack(const mcf_pack_t* __restrict__ table, PackPtrs ptrs, uint
   }
 }
 
+__global__ void k_unpack(const mcf_unpack_t* __restrict__ table, const float* __restrict__ staging,
+                         float* __restrict__ grads) {
+  const mcf_unpack_t e = table[blockIdx.x];
+  const int n = e.nrows * e.ncols;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = i / e.ncols, c = i - r * e.ncols;
+    const float v = e.transposed ? staging[e.src_off + (long long)c * e.src_ld + r]
+                                 : staging[e.src_off + (long long)r * e.src_ld + c];
+    grads[e.dst_off + (long long)r * e.dst_ld + c] = v;
+  }
+}
+
+__global__ void k_colsum(const float* __restrict__ src, long long n_rows, int stride, int ncols,
+                         float* __restrict__ out) {
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < n_rows;
+       m += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c < ncols) acc[c] += src[m * stride + c];
+  }
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    float v = acc[c];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && c < ncols) atomicAdd(out + c, v);
+  }
+}
+
 }  // namespace mcf
 
 extern "C" {
+
+int mcf_unpack(const mcf_unpack_t* table_dev, int n_entries, const float* staging, float* grads,
+               cudaStream_t stream) {
+  if (n_entries <= 0) return 0;
+  mcf::k_unpack<<<n_entries, 256, 0, stream>>>(table_dev, staging, grads);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+int mcf_colsum(const float* src, long long n_rows, int stride, int ncols, float* out, cudaStream_t stream) {
+  if (n_rows <= 0) return 0;
+  if (ncols < 1 || ncols > 16) return MCF_ERR_BAD_ARG;
+  long long blocks = (n_rows + 255) / 256;
+  if (blocks > 592) blocks = 592;
+  mcf::k_colsum<<<(unsigned)blocks, 256, 0, stream>>>(src, n_rows, stride, ncols, out);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
 
 int mcf_abi_version(void) { return MCF_ABI_VERSION; }
 

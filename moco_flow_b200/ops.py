@@ -308,6 +308,7 @@ def chain_params(pp: PackedPlan, n_rows: int, rows_per_ray: int, n_rays: int) ->
     cp.n_rows, cp.rows_per_ray, cp.n_rays = n_rows, rows_per_ray, n_rays
     cp.x0_save_off = L.NONE
     cp.fwd_x0_off = cp.fwd_he_off = L.NONE
+    cp.extra_save_off = cp.dhead_save_off = L.NONE
     cp.out_stride, cp.sigma_col = 4, 3
     return cp
 

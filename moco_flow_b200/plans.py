@@ -219,3 +219,220 @@ def nof_forward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: i
 def folded_layers(D: int, skips: Sequence[int]) -> List[int]:
     """0-based trunk layers of a NoF whose extra-feature columns are folded, in raybias order."""
     return [i for i in range(D) if i == 0 or i in skips]
+
+
+# ================================================================================================
+# backward: dX chain programs and weight-gradient job lists
+# ================================================================================================
+@dataclass
+class GradJob:
+    """One mcf_dw_gemm call: staging[i][j] = sum_rows P[row][i] * Q[row][j]."""
+    p_src: str      # 'fwd' | 'bwd' save record
+    p_off: int
+    p_cols: int
+    q_src: str
+    q_off: int
+    q_cols: int
+    st_off: int     # float offset into the staging buffer
+    ld: int
+    n_i: int
+    n_j: int
+    colsum_off: int  # float offset in staging of colsum_p, or -1
+    params: tuple    # parameter names this job feeds
+
+
+@dataclass
+class GradPlan:
+    jobs: List[GradJob]
+    unpack: np.ndarray           # UNPACK_DT entries staging -> flat gradient buffer
+    staging_floats: int
+    head_colsum: tuple           # (ncols, stride, staging float offset) of the fp32 head-gradient column sums
+    param_names: List[str]
+    param_offsets: Dict[str, int]
+    param_shapes: Dict[str, tuple]
+    total_floats: int
+
+
+class _GradBuilder:
+    def __init__(self, shapes: Dict[str, tuple]):
+        self.jobs: List[GradJob] = []
+        self.unpack: List[tuple] = []
+        self.st = 0
+        self.names = list(shapes)
+        self.shapes = dict(shapes)
+        self.offsets, off = {}, 0
+        for n, shp in shapes.items():
+            self.offsets[n] = off
+            off += _ceil(int(np.prod(shp)), 4) * 4
+        self.total = off
+
+    def alloc(self, n: int) -> int:
+        off = self.st
+        self.st += _ceil(n, 4) * 4
+        return off
+
+    def job(self, P, Q, n_i, n_j, params, colsum=False) -> GradJob:
+        n_j4 = _ceil(n_j, 4) * 4
+        ld = n_j4
+        st = self.alloc(n_i * ld)
+        cs = self.alloc(n_i) if colsum else -1
+        j = GradJob(P[0], P[1], P[2], Q[0], Q[1], Q[2], st, ld, n_i, n_j4, cs, tuple(params))
+        self.jobs.append(j)
+        return j
+
+    def scatter(self, src_off, src_ld, name, row0, col0, nrows, ncols, transposed=False):
+        shp = self.shapes[name]
+        dst_ld = shp[1] if len(shp) == 2 else shp[0]
+        dst = self.offsets[name] + (row0 * dst_ld + col0 if len(shp) == 2 else col0)
+        self.unpack.append((src_off, dst, src_ld, dst_ld, nrows, ncols, int(transposed), 0))
+
+    def finish(self, head_colsum) -> GradPlan:
+        return GradPlan(self.jobs, np.array(self.unpack, dtype=L.UNPACK_DT), max(self.st, 4), head_colsum,
+                        self.names, self.offsets, self.shapes, self.total)
+
+
+def _bwd_trunk(b: _Builder, fwd: Plan, D: int, W: int, cx: int, skips, skip_extra: int, prefix: str,
+               need_dx: bool) -> None:
+    """Rounds that take dY_D (already in H) down to dY_1 (and the PE gradient)."""
+    nkb, NH = W // 64, W // 128
+    cin_extra = cx + skip_extra
+    for i in range(D - 1, -1, -1):
+        wname = f"{prefix}_{i+1}.0.weight"
+        is_skip = i in skips and i > 0
+        ld = cin_extra if i == 0 else (W + cin_extra if is_skip else W)
+        if (i == 0 or is_skip) and need_dx:
+            c0 = len(b.chunks)
+            for kb in range(nkb):
+                img = b.image(wname, 0, cx, 64 * kb, 64, ld, True, 64)
+                b.chunk(img, 1, kb, 4, 64, 0, init=(kb == 0))
+            b.round(L.EPI_B_DPE, 64, 0, c0, aux_off=(1 if i == 0 else 0))
+        if i == 0:
+            break
+        base = cin_extra if is_skip else 0
+        c0 = len(b.chunks)
+        for kb in range(nkb):
+            for nh in range(NH):
+                img = b.image(wname, base + nh * 128, 128, 64 * kb, 64, ld, True, 128)
+                b.chunk(img, 1, kb, 4, 128, nh * 128, init=(kb == 0))
+        b.round(L.EPI_B_MASK, W, 0, c0, save_off=b.save_slot(f"dy{i}", nkb), mask_off=fwd.offsets[f"mask_h{i}"])
+
+
+def nerf_backward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: int, need_dx: bool,
+                       fwd: Plan) -> Plan:
+    """dX chain of models/nerf.py:61-102 (autograd of the forward program)."""
+    _check_common(W, cx)
+    if W != 256:
+        raise ValueError("NeRF training through the fused kernels requires W == 256")
+    b = _Builder(W)
+    nkb, NH, half = W // 64, W // 128, W // 2
+    b.save_slot("dhead", 1)
+    b.save_slot("dye", _ceil(half, 64))
+    # round 0: through extra_encoding (feat part)
+    c0 = len(b.chunks)
+    for kb in range(_ceil(half, 64)):
+        for nh in range(NH):
+            img = b.image("extra_encoding.0.weight", nh * 128, 128, 64 * kb, 64, W + extra_dim, True, 128)
+            b.chunk(img, 1, kb, 4, 128, nh * 128, init=(kb == 0))
+    wrgb = b.const("rgb.0.weight", 0, 3, 0, half, half)
+    b.round(L.EPI_B_LINEAR, W, 0, c0, aux_off=wrgb, save_off=b.save_slot("dyf", nkb),
+            mask_off=fwd.offsets["mask_he"])
+    # round 1: through xyz_encoding_final, add the sigma head, mask with h_D
+    c0 = len(b.chunks)
+    for kb in range(nkb):
+        for nh in range(NH):
+            img = b.image("xyz_encoding_final.weight", nh * 128, 128, 64 * kb, 64, W, True, 128)
+            b.chunk(img, 1, kb, 4, 128, nh * 128, init=(kb == 0))
+    wsig = b.const("sigma.weight", 0, 1, 0, W, W)
+    b.round(L.EPI_B_MASK_SIGMA, W, 0, c0, aux_off=wsig, save_off=b.save_slot(f"dy{D}", nkb),
+            mask_off=fwd.offsets[f"mask_h{D}"])
+    _bwd_trunk(b, fwd, D, W, cx, tuple(skips), 0, "xyz_encoding", need_dx)
+    return b.finish()
+
+
+def nof_backward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: int, use_quat: bool,
+                      need_dx: bool, fwd: Plan) -> Plan:
+    """dX chain of models/nof.py:55-85."""
+    _check_common(W, cx)
+    b = _Builder(W)
+    nkb, NH = W // 64, W // 128
+    n_head = 9 if use_quat else 3
+    b.save_slot("ghead", 1)
+    c0 = len(b.chunks)
+    for nh in range(NH):
+        img = b.image("nof_encoding_final.weight", nh * 128, 128, 0, n_head, W, True, 128)
+        b.chunk(img, 1, 0, 1, 128, nh * 128, init=True)
+    b.round(L.EPI_B_MASK, W, 0, c0, save_off=b.save_slot(f"dy{D}", nkb), mask_off=fwd.offsets[f"mask_h{D}"])
+    _bwd_trunk(b, fwd, D, W, cx, tuple(skips), extra_dim, "nof_encoding", need_dx)
+    return b.finish()
+
+
+def nerf_grad_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: int, shapes: Dict[str, tuple],
+                   fwd: Plan, bwd: Plan) -> GradPlan:
+    g = _GradBuilder(shapes)
+    half = W // 2
+    F = lambda key, cols: ("fwd", fwd.offsets["save_" + key], cols)
+    B = lambda key, cols: ("bwd", bwd.offsets["save_" + key], cols)
+    for i in range(D):
+        wn, bn = f"xyz_encoding_{i+1}.0.weight", f"xyz_encoding_{i+1}.0.bias"
+        P = B(f"dy{i+1}", W)
+        is_skip = i in skips and i > 0
+        first = True
+        if i == 0 or is_skip:
+            j = g.job(P, F("x0", 64), W, 64, (wn, bn), colsum=True)
+            g.scatter(j.st_off, j.ld, wn, 0, 0, W, cx)
+            g.scatter(j.colsum_off, W, bn, 0, 0, 1, W)
+            first = False
+        if i > 0:
+            j = g.job(P, F(f"h{i}", W), W, W, (wn, bn), colsum=first)
+            g.scatter(j.st_off, j.ld, wn, 0, cx if is_skip else 0, W, W)
+            if first:
+                g.scatter(j.colsum_off, W, bn, 0, 0, 1, W)
+    j = g.job(B("dyf", W), F(f"h{D}", W), W, W, ("xyz_encoding_final.weight", "xyz_encoding_final.bias"), colsum=True)
+    g.scatter(j.st_off, j.ld, "xyz_encoding_final.weight", 0, 0, W, W)
+    g.scatter(j.colsum_off, W, "xyz_encoding_final.bias", 0, 0, 1, W)
+    en, eb = "extra_encoding.0.weight", "extra_encoding.0.bias"
+    j = g.job(B("dye", half), F("feat", W), half, W, (en, eb), colsum=True)
+    g.scatter(j.st_off, j.ld, en, 0, 0, half, W)
+    g.scatter(j.colsum_off, half, eb, 0, 0, 1, half)
+    if extra_dim > 0:
+        j = g.job(B("dye", half), F("extra", 64), half, 64, (en,))
+        g.scatter(j.st_off, j.ld, en, 0, W, half, extra_dim)
+    j = g.job(F("he", half), B("dhead", 64), half, 4, ("rgb.0.weight",))
+    g.scatter(j.st_off, j.ld, "rgb.0.weight", 0, 0, 3, half, transposed=True)
+    j = g.job(F(f"h{D}", W), B("dhead", 64), W, 4, ("sigma.weight",))
+    g.scatter(j.st_off + 3, j.ld, "sigma.weight", 0, 0, 1, W, transposed=True)
+    hc = g.alloc(4)
+    g.scatter(hc, 4, "rgb.0.bias", 0, 0, 1, 3)
+    g.scatter(hc + 3, 4, "sigma.bias", 0, 0, 1, 1)
+    return g.finish((4, 4, hc))
+
+
+def nof_grad_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: int, use_quat: bool,
+                  shapes: Dict[str, tuple], fwd: Plan, bwd: Plan) -> GradPlan:
+    g = _GradBuilder(shapes)
+    n_head = 9 if use_quat else 3
+    F = lambda key, cols: ("fwd", fwd.offsets["save_" + key], cols)
+    B = lambda key, cols: ("bwd", bwd.offsets["save_" + key], cols)
+    for i in range(D):
+        wn, bn = f"nof_encoding_{i+1}.0.weight", f"nof_encoding_{i+1}.0.bias"
+        P = B(f"dy{i+1}", W)
+        is_skip = i in skips and i > 0
+        first = True
+        if i == 0 or is_skip:
+            # Q = [x0 block | per-ray feature block] (adjacent in the forward save record)
+            j = g.job(P, F("x0", 128), W, 128, (wn, bn), colsum=True)
+            g.scatter(j.st_off, j.ld, wn, 0, 0, W, cx)
+            if extra_dim > 0:
+                g.scatter(j.st_off + 64, j.ld, wn, 0, cx, W, extra_dim)
+            g.scatter(j.colsum_off, W, bn, 0, 0, 1, W)
+            first = False
+        if i > 0:
+            j = g.job(P, F(f"h{i}", W), W, W, (wn, bn), colsum=first)
+            g.scatter(j.st_off, j.ld, wn, 0, (cx + extra_dim) if is_skip else 0, W, W)
+            if first:
+                g.scatter(j.colsum_off, W, bn, 0, 0, 1, W)
+    j = g.job(F(f"h{D}", W), B("ghead", 64), W, 12, ("nof_encoding_final.weight",))
+    g.scatter(j.st_off, j.ld, "nof_encoding_final.weight", 0, 0, n_head, W, transposed=True)
+    hc = g.alloc(12)
+    g.scatter(hc, 12, "nof_encoding_final.bias", 0, 0, 1, n_head)
+    return g.finish((n_head, 12, hc))

@@ -460,7 +460,7 @@ def linear_init(rng, out_f: int, in_f: int):
 
 def make_nerf_params(spec: NeRFSpec, seed: int, dense: bool = False) -> Dict[str, Tensor]:
     """Random-init NeRF state-dict (reference names/shapes, models/nerf.py:28-59).  ``dense``
-    scales the sigma head so that opacities are non-degenerate."""
+    re-centres and scales the sigma head so that opacities are non-degenerate."""
     rng = _np_rng(seed)
     p: Dict[str, Tensor] = {}
     for i in range(spec.D):
@@ -472,8 +472,17 @@ def make_nerf_params(spec: NeRFSpec, seed: int, dense: bool = False) -> Dict[str
     p["sigma.weight"], p["sigma.bias"] = linear_init(rng, 1, spec.W)
     p["rgb.0.weight"], p["rgb.0.bias"] = linear_init(rng, 3, spec.W // 2)
     if dense:
-        p["sigma.weight"] = p["sigma.weight"] * 400.0
-        p["sigma.bias"] = torch.zeros_like(p["sigma.bias"])
+        # Centre and scale the density head on a fixed probe set so that sigma straddles zero with
+        # std ~40: alphas then cover (0,1) instead of the all-empty / all-opaque volumes that the
+        # default init gives.
+        nf = max((spec.in_channels_xyz // 3 - 1) // 2, 0)
+        probe = torch.from_numpy(rng.uniform([-0.5, -1.0, -0.3], [0.5, 1.0, 0.3], size=(2048, 3)).astype("float32"))
+        feats = _padded(positional_encoding(probe, PESpec(3, nf)), spec.in_channels_xyz)
+        with torch.no_grad():
+            raw = nerf_mlp(p, spec, feats, sigma_only=True)
+        gain = 40.0 / float(raw.std().clamp_min(1e-6))
+        p["sigma.weight"] = p["sigma.weight"] * gain
+        p["sigma.bias"] = (p["sigma.bias"] - raw.mean()) * gain
         p["rgb.0.weight"] = p["rgb.0.weight"] * 8.0
     return p
 

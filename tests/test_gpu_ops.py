@@ -140,7 +140,13 @@ def test_sample_pdf_level2_fused_cdf(dev):
     cdf_ulp = (cdf.cpu() != aux["cdf"]).float().mean().item()
     print(f"sample_pdf fused: index mismatches {mism}/{R*Sf}, cdf entries differing {cdf_ulp:.4%}")
     assert mism <= 4
-    assert (s.cpu() - ref).abs().max().item() <= 2e-6
+    # a 1-ulp cdf difference moves a sample by at most ulp/denom of its bin width (ill-conditioned only for
+    # near-empty bins, where any position inside the bin is as good): bound the deviation accordingly
+    c_lo, c_hi = aux["cdf"].gather(1, aux["below"]), aux["cdf"].gather(1, aux["above"])
+    b_lo, b_hi = mid.gather(1, aux["below"]), mid.gather(1, aux["above"])
+    denom = (c_hi - c_lo).clamp_min(1e-5)
+    bound = 2e-6 + 4 * 1.2e-7 / denom * (b_hi - b_lo)
+    assert bool(((s.cpu() - ref).abs() <= bound).all())
     # merged output is the sorted concatenation (values are copies, so sortedness + multiset equality is exact)
     exp = torch.sort(torch.cat([z, s.cpu()], dim=1), dim=1).values
     assert torch.equal(merged.cpu(), exp)
