@@ -132,18 +132,14 @@ def test_nerf_fused_pe_many_tiles(dev):
     assert e <= 1e-2 * sc
 
 
-@pytest.mark.parametrize("name", ["cfg1_nerf_only", "moco_test_time", "coarse_only", "init_nerf_dir"])
-def test_render_rays_forward_golden(dev, golden_dir, name):
-    """render_rays (no grad) against the reference-generated fixtures."""
+def _build_cuda_models(dev, nerfs, nofs, nerf_pes, nof_pes):
     import moco_flow_b200 as mf
     from tests.helpers import pe_module
-    g = dict(np.load(os.path.join(golden_dir, f"render_{name}.npz")))
-    rays, bg, nerf_pes, nerfs, nof_pes, nofs, kw = build_case(name, g)
     spec = nerfs[0].spec
     models = []
     for b in nerfs:
         m = mf.NeRF(spec.D, spec.W, spec.in_channels_xyz, list(spec.skips), spec.extra_feat_type, spec.extra_feat_dim)
-        m.load_state_dict(b.params)
+        m.load_state_dict({k: v.detach() for k, v in b.params.items()})
         models.append(m.to(dev))
     nof_models = None
     if nofs:
@@ -151,26 +147,93 @@ def test_render_rays_forward_golden(dev, golden_dir, name):
         for b in nofs:
             s = b.spec
             m = mf.NoF(s.D, s.W, s.in_channels_xyz, list(s.skips), s.extra_feat_type, s.extra_feat_dim, s.use_quat)
-            m.load_state_dict(b.params)
+            m.load_state_dict({k: v.detach() for k, v in b.params.items()})
             nof_models.append(m.to(dev))
     nerf_embs = [pe_module(pp, mf.Embedding) if pp is not None else None for pp in nerf_pes]
     nof_embs = [pe_module(pp, mf.Embedding) for pp in nof_pes] if nof_pes else None
+    return models, nof_models, nerf_embs, nof_embs
+
+
+FWD_CASES = ["cfg1_nerf_only", "moco_test_time", "coarse_only", "init_nerf_dir", "moco_train", "moco_train_noise",
+             "default_init"]
+
+
+@pytest.mark.parametrize("name", FWD_CASES)
+def test_render_rays_forward(dev, golden_dir, name):
+    """render_rays (no grad), two tiers:
+      (1) exactness -- against the oracle run with bf16 tensor-core emulation (same arithmetic as the kernels);
+      (2) north-star tolerance -- against the reference-generated fp32 fixtures: <= 2e-3 on rgb / opacity / depth.
+    depth_fine passes through the reference's resampling step (sample_pdf on the coarse weights), a discontinuous
+    map: a bf16-level change of the coarse weights can move a fine sample into another bin, so for depth_fine
+    the fp32 comparison asserts the median over rays at 2e-3 and bounds the max loosely; tier (1) is tight for it."""
+    import moco_flow_b200 as mf
+    g = dict(np.load(os.path.join(golden_dir, f"render_{name}.npz")))
+    rays, bg, nerf_pes, nerfs, nof_pes, nofs, kw = build_case(name, g)
+    models, nof_models, nerf_embs, nof_embs = _build_cuda_models(dev, nerfs, nofs, nerf_pes, nof_pes)
     dr = kw.pop("draws")
     draws = mf.Draws(*(None if t is None else t.to(dev) for t in (dr.perturb, dr.noise_coarse, dr.u, dr.noise_fine)))
     with torch.no_grad():
         res = mf.render_rays(rays.to(dev), bg.to(dev), nerf_embs, models, nof_embeddings=nof_embs,
                              nof_models=nof_models, draws=draws, **kw)
+        orc.EMULATE_BF16 = True
+        try:
+            emu = orc.render_rays(rays, bg, nerf_pes, nerfs, nof_pes, nofs, draws=dr, **kw)
+        finally:
+            orc.EMULATE_BF16 = False
     torch.cuda.synchronize()
     _no_device_error()
     keys = sorted(k[4:] for k in g if k.startswith("out_"))
     assert sorted(res.keys()) == keys
     for k in keys:
-        ref = T(g["out_" + k])
-        assert tuple(res[k].shape) == tuple(ref.shape), k
-        e, sc = stats(f"{name}.{k}", res[k], ref)
+        ref, em = T(g["out_" + k]), emu[k]
+        got = res[k].cpu()
+        if "disp" in k:
+            # dynamic-length vectors (alpha >= 0.01 mask): same selection as the emulated oracle, fp32 means close
+            assert tuple(got.shape) == tuple(em.shape), (k, got.shape, em.shape)
+            e, sc = stats(f"{name}.{k} vs bf16-emulated", got, em)
+            assert e <= 1e-3 * max(sc, 1e-2), k
+            assert abs(got.mean().item() - ref.mean().item()) <= 2e-2 * max(ref.mean().abs().item(), 1e-3), k
+            continue
+        assert tuple(got.shape) == tuple(ref.shape), k
+        e_emu, sc = stats(f"{name}.{k} vs bf16-emulated", got, em)
+        e_ref, _ = stats(f"{name}.{k} vs fp32 reference", got, ref)
+        rel = ((got - ref).abs() / ref.abs().clamp_min(1e-3))
         if k.startswith("rgb") or k.startswith("opacity"):
-            assert e <= 2e-3, k          # north star: <= 2e-3 on rgb for the bf16 MLP path
-        elif k.startswith("depth"):
-            assert e <= 2e-3 * max(sc, 1.0), k   # <= 2e-3 relative on depth
-        else:
-            assert e <= 5e-3 * max(sc, 1e-2), k
+            assert e_emu <= 3e-4, k
+            assert e_ref <= 2e-3, k                      # north star: <= 2e-3 on rgb for the bf16 MLP path
+        elif k == "depth_coarse":
+            assert e_emu <= 3e-4 * max(sc, 1.0), k
+            assert rel.max().item() <= 2e-3, k           # north star: <= 2e-3 (relative) on depth
+        else:  # depth_fine
+            assert e_emu <= 1e-3 * max(sc, 1.0), k
+            assert rel.median().item() <= 2e-3, k
+            assert rel.max().item() <= 5e-2, k
+
+
+def test_fine_pass_at_reference_samples(dev, golden_dir):
+    """The fine NeRF pass evaluated at the reference's own fine sample depths (no resampling in between):
+    rgb / depth within the north-star 2e-3 against the fp32 oracle."""
+    import moco_flow_b200 as mf
+    name = "moco_train"
+    g = dict(np.load(os.path.join(golden_dir, f"render_{name}.npz")))
+    rays, bg, nerf_pes, nerfs, nof_pes, nofs, kw = build_case(name, g)
+    models, nof_models, nerf_embs, nof_embs = _build_cuda_models(dev, nerfs, nofs, nerf_pes, nof_pes)
+    with torch.no_grad():
+        ref = orc.render_rays(rays, bg, nerf_pes, nerfs, nof_pes, nofs, return_aux=True, **kw)
+        z_fine = ref["_aux"]["z_fine"]
+        x_f = rays[:, None, 0:3] + rays[:, None, 3:6] * z_fine[:, :, None]
+        x_can = orc.nof_inference(x_f, rays[:, 8:9], nof_pes[0], nof_pes[1], nofs[0])
+        noise = kw["draws"].noise_fine
+        rgb_o, dep_o, w_o, a_o = orc.nerf_inference(x_can, rays[:, 8:9], rays[:, 3:6], z_fine, noise * kw["noise_std"],
+                                                    nerf_pes, nerfs[1], background=bg)
+        xc = mf.nof_inference(x_f.to(dev), rays[:, 8:9].to(dev), nof_embs, nof_models[0])
+        rgb, dep, w, a = mf.nerf_inference(xc, rays[:, 8:9].to(dev), rays[:, 3:6].to(dev), z_fine.to(dev),
+                                           kw["noise_std"], nerf_embs, models[1], background=bg.to(dev),
+                                           noise=noise.to(dev))
+    e, _ = stats("fine pass @ reference samples: rgb", rgb, rgb_o)
+    assert e <= 2e-3
+    rel = ((dep.cpu() - dep_o).abs() / dep_o.abs()).max().item()
+    print(f"[parity] fine pass @ reference samples: depth max rel {rel:.3e}")
+    assert rel <= 2e-3
+    e, _ = stats("fine pass @ reference samples: weights", w, w_o)
+    assert e <= 5e-3
