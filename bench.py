@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Benchmark of the MoCo-Flow ray-rendering hot path (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|render]
+
+A step of the default workload (BASELINE.json configs[2], the one the headline metric "train rays/s
+(fwd+bwd, 64+64 spp)" is quoted on) is one MoCo-Flow training step on 4096 synthetic rays per GPU:
+render_rays with both flow chains (5 NoF + 1 NeRF evaluations per sample, coarse 64 + fine 64 samples),
+image MSE + 0.2 local + 0.2 global chain losses, backward, NCCL all-reduce of the flat gradient buffer
+(N > 1) and one Adam step.  ``--workload render`` times configs[1] (4096-ray inference render).
+
+Prints ONE JSON line.  ``--impl reference`` times the CPU oracle port of the reference on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+RAYS_PER_GPU = 4096
+N_COARSE, N_FINE = 64, 64
+N_FRAMES = 160
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic workload (shared by both arms)
+# --------------------------------------------------------------------------------------------------
+def synth_batch(n_rays: int, seed: int):
+    from oracle import moco_oracle as orc
+    import numpy as np
+    rays = orc.make_rays(n_rays, seed=seed, n_frames=N_FRAMES, chained=True)
+    g = np.random.Generator(np.random.PCG64(seed + 1000))
+    target = torch.from_numpy(g.uniform(0, 1, size=(n_rays, 3)).astype("float32"))
+    bg = torch.ones(n_rays, 3)
+    return rays, bg, target
+
+
+def algorithmic_flops_per_ray(workload: str) -> float:
+    """un-padded reference shapes, 2*MAC; backward counted as 2x forward."""
+    nerf, nerf_sigma, nof = 1181184.0, 982528.0, 134400.0
+    if workload == "render":  # test_time: sigma-only coarse + full fine, bw-NoF on every sample
+        return nof * (N_COARSE + N_COARSE + N_FINE) + nerf_sigma * N_COARSE + nerf * (N_COARSE + N_FINE)
+    s_tot = N_COARSE + (N_COARSE + N_FINE)
+    return 3.0 * (5 * nof * s_tot + nerf * s_tot)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+class Clocks:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx = float(f[2])
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        except OSError:
+            pass
+        if sm:
+            # under load = the upper half of the samples (the sampler also sees idle gaps around the region)
+            sm_sorted = sorted(sm)
+            out.update(sm_mhz=statistics.median(sm_sorted[len(sm_sorted) // 2:]), sm_max_mhz=mx,
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def build_models(dev, seed: int = 0):
+    import moco_flow_b200 as mf
+    torch.manual_seed(seed)  # random-init weights of the c2f.yaml shapes (configs/.../c2f.yaml:44-102)
+    nerfs = [mf.NeRF(8, 256, 63, [4], "ind", 5).to(dev) for _ in range(2)]
+    nofs = [mf.NoF(4, 128, 33, [2], "ind", 33, True).to(dev) for _ in range(2)]
+    nerf_embs = [mf.Embedding(3, 10), mf.Embedding(1, 2), None]
+    nof_embs = [mf.Embedding(3, 5), mf.Embedding(1, 16)]
+    return nerfs, nofs, nerf_embs, nof_embs
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import moco_flow_b200 as mf
+    from moco_flow_b200 import _lib as L
+    from moco_flow_b200 import dp
+    from moco_flow_b200.build import build
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    if rank == 0:
+        build()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    L.lib()
+    nerfs, nofs, nerf_embs, nof_embs = build_models(dev)
+    dp.broadcast_parameters(nerfs + nofs)
+    train = args.workload == "train"
+    R = RAYS_PER_GPU
+    # this rank's shard of the step's global batch (N * 4096 rays): weak scaling
+    rays_h, bg_h, tgt_h = synth_batch(R, seed=1 + rank)
+    rays_h, bg_h, tgt_h = rays_h.pin_memory(), bg_h.pin_memory(), tgt_h.pin_memory()
+    rays_d, bg_d, tgt_d = rays_h.to(dev), bg_h.to(dev), tgt_h.to(dev)
+    flat = dp.FlatGradients(nerfs + nofs) if train else None
+    opt = torch.optim.Adam(flat.params, lr=5e-4, eps=1e-8, fused=True) if train else None
+    loss_fn = mf.MSELoss()
+
+    def step(rays, bg, tgt):
+        if train:
+            flat.zero()
+            res = mf.render_rays(rays, bg, nerf_embs, nerfs, nof_embeddings=nof_embs, nof_models=nofs,
+                                 chain_local=True, chain_global=True, N_samples=N_COARSE, N_importance=N_FINE,
+                                 perturb=1.0, noise_std=0.0, fused_residual_mean=True)
+            loss = loss_fn(res, tgt)
+            loss = loss + 0.2 * (res["nof_local_disp_coarse"].mean() + res["nof_local_disp_fine"].mean())
+            loss = loss + 0.2 * (res["nof_global_disp_coarse"].mean() + res["nof_global_disp_fine"].mean())
+            loss.backward()
+            flat.allreduce_mean()
+            opt.step()
+            return loss.detach()
+        with torch.no_grad():
+            res = mf.render_rays(rays, bg, nerf_embs, nerfs, nof_embeddings=nof_embs, nof_models=nofs,
+                                 N_samples=N_COARSE, N_importance=N_FINE, perturb=1.0, noise_std=0.0, test_time=True)
+        return res["rgb_fine"].mean()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(rays_d, bg_d, tgt_d)
+    sync_all()
+
+    # ---- device-resident timing (value) ----
+    clocks = Clocks(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    sync_all()
+    launches0 = L.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(rays_d, bg_d, tgt_d)
+    e1.record()
+    sync_all()
+    launches = L.LAUNCHES - launches0
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- end-to-end timing through the public API with host buffers ----
+    sync_all()
+    loss_host = torch.empty((), pin_memory=True)
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        r = rays_h.to(dev, non_blocking=True)
+        b = bg_h.to(dev, non_blocking=True)
+        t = tgt_h.to(dev, non_blocking=True)
+        out = step(r, b, t)
+        loss_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    t1.record()
+    sync_all()
+    ms_e2e = t0.elapsed_time(t1)
+
+    # ---- per-kernel event timing for the roofline (extra steps, not part of the numbers above) ----
+    L.PROFILE = []
+    for _ in range(2):
+        step(rays_d, bg_d, tgt_d)
+    torch.cuda.synchronize()
+    prof, L.PROFILE = L.PROFILE, None
+    agg = {}
+    for tag, work, unit, a, b_ in prof:
+        d = agg.setdefault(tag, dict(ms=0.0, work=0.0, unit=unit, n=0))
+        d["ms"] += a.elapsed_time(b_)
+        d["work"] += work
+        d["n"] += 1
+
+    times = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = times.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json: sustained bf16, copy HBM)" if peaks else "fallback (B200_PROFILING.md)"
+    total_rays = world * R * args.steps
+    kernels = {}
+    for tag, d in agg.items():
+        rate = d["work"] / (d["ms"] * 1e-3) if d["ms"] > 0 else 0.0
+        kernels[tag] = {"launches_per_step": d["n"] // 2, "ms_per_step": round(d["ms"] / 2, 4),
+                        "achieved": round(rate / (1e12 if d["unit"] == "flop" else 1e9), 2),
+                        "unit": "TFLOP/s" if d["unit"] == "flop" else "GB/s"}
+    dom = max(agg.items(), key=lambda kv: kv[1]["ms"])[0] if agg else None
+    roofline = None
+    if dom:
+        d = agg[dom]
+        tensor = d["unit"] == "flop"
+        ach = d["work"] / (d["ms"] * 1e-3) / (1e12 if tensor else 1e9)
+        pk = tensor_peak if tensor else hbm_peak
+        roofline = {"kernel": dom, "bound": "tensor" if tensor else "hbm", "achieved": round(ach, 2), "peak": pk,
+                    "unit": "TFLOP/s" if tensor else "GB/s", "frac": round(ach / pk, 4), "traffic": None,
+                    "peak_source": peak_src, "share_of_step": round(d["ms"] / sum(v["ms"] for v in agg.values()), 3)}
+    flops_ray = algorithmic_flops_per_ray(args.workload)
+    h2d = int(rays_h.numel() + bg_h.numel() + tgt_h.numel()) * 4
+    line = {
+        "metric": "train rays/s (fwd+bwd, 64+64 spp)" if train else "render rays/s (64+64 spp, test_time)",
+        "value": round(total_rays / (ms * 1e-3), 1), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": ("MoCo-Flow training step fwd+bwd (BASELINE configs[2]): 4096 rays/GPU, 64+64 samples, "
+                                "bw/fw NoF chains (local+global), random-init c2f.yaml shapes, Adam step, "
+                                "ray-sharded DP + flat-gradient NCCL all-reduce") if train else
+                               ("full MoCo-Flow ray render (BASELINE configs[1]): 4096 rays, 64+64 samples, test_time"),
+                   "rays_per_gpu": R, "n_coarse": N_COARSE, "n_fine": N_FINE,
+                   "l2": "no flush: the step streams > 5 GB of saved operand images per GPU, far above the 126 MB L2",
+                   "parallelism": f"dp{world} (rays sharded, weights replicated)"},
+        "e2e": {"value": round(total_rays / (ms_e2e * 1e-3), 1), "unit": "rays/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": roofline,
+        "kernels": kernels,
+        "model_tflops": round(total_rays * flops_ray / (ms * 1e-3) / 1e12, 2),
+        "model_tensor_frac": round(total_rays * flops_ray / (ms * 1e-3) / 1e12 / (tensor_peak * world), 4),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.workload, sample_rays=args.cpu_rays, steps=1, warmup=1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_step_fn(workload: str, n_rays: int):
+    from oracle import moco_oracle as orc
+    torch.manual_seed(0)
+    pes = orc.C2F_PE
+    nerf_p = [orc.make_nerf_params(orc.C2F_NERF, s) for s in (1, 2)]
+    nof_p = [orc.make_nof_params(orc.C2F_NOF, s) for s in (3, 4)]
+    train = workload == "train"
+    if train:
+        for p in nerf_p + nof_p:
+            for k in p:
+                p[k].requires_grad_(True)
+    nerfs = [orc.NeRFBundle(orc.C2F_NERF, p) for p in nerf_p]
+    nofs = [orc.NoFBundle(orc.C2F_NOF, p) for p in nof_p]
+    rays, bg, tgt = synth_batch(n_rays, seed=1)
+    params = [v for p in nerf_p + nof_p for v in p.values()]
+    opt = torch.optim.Adam(params, lr=5e-4, eps=1e-8) if train else None
+
+    def step():
+        if train:
+            opt.zero_grad(set_to_none=True)
+            res = orc.render_rays(rays, bg, [pes["nerf_xyz"], pes["nerf_ind"], None], nerfs,
+                                  [pes["nof_xyz"], pes["nof_ind"]], nofs, chain_local=True, chain_global=True,
+                                  N_samples=N_COARSE, N_importance=N_FINE, perturb=1.0, noise_std=0.0)
+            loss = orc.train_objective(res, tgt)
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+        with torch.no_grad():
+            res = orc.render_rays(rays, bg, [pes["nerf_xyz"], pes["nerf_ind"], None], nerfs,
+                                  [pes["nof_xyz"], pes["nof_ind"]], nofs, N_samples=N_COARSE, N_importance=N_FINE,
+                                  perturb=1.0, noise_std=0.0, test_time=True)
+        return float(res["rgb_fine"].mean())
+    return step
+
+
+def cpu_baseline(workload: str, sample_rays: int, steps: int, warmup: int):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(workload, sample_rays)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(sample_rays / dt, 2), "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_rays} rays of the same workload per step ({steps} timed step(s), {warmup} warm-up), "
+                      f"{dt:.2f} s/step; the reference is a Python/PyTorch code base, so the CPU arm is the oracle "
+                      f"port (oracle/moco_oracle.py, torch fp32 eager, all host threads)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = args.cpu_rays
+    step = cpu_step_fn(args.workload, n)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    train = args.workload == "train"
+    val = round(n * args.steps / dt, 2)
+    sample = (f"each step = {n} rays of the workload (bounded sample of the 4096-ray step; cost is linear in rays), "
+              f"oracle port on {torch.get_num_threads()} host threads")
+    line = {
+        "impl": "reference",
+        "metric": "train rays/s (fwd+bwd, 64+64 spp)" if train else "render rays/s (64+64 spp, test_time)",
+        "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "same workload as the default arm, CPU oracle port of the reference", "rays_per_step": n,
+                   "n_coarse": N_COARSE, "n_fine": N_FINE},
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "render"])
+    ap.add_argument("--cpu-rays", type=int, default=256, help="rays per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

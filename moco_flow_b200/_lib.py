@@ -91,7 +91,34 @@ def lib():
     return _lib
 
 
+# ---- instrumentation used by bench.py ----------------------------------------------------------------
+LAUNCHES = 0      # C-ABI kernel-launching calls issued so far (every entry except the two query calls)
+PROFILE = None    # when a list: (tag, work, unit, start_event, end_event) per timed launch
+
+
+class timed:
+    """Brackets one launch with CUDA events on the current stream when profiling is switched on."""
+
+    def __init__(self, tag: str, work: float, unit: str):
+        self.tag, self.work, self.unit = tag, work, unit
+
+    def __enter__(self):
+        if PROFILE is not None:
+            import torch
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.ev[1].record()
+            PROFILE.append((self.tag, self.work, self.unit, self.ev[0], self.ev[1]))
+        return False
+
+
 def check(code: int, what: str) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     if code != 0:
         kind = "cudaError" if code > 0 else "MCF_ERR"
         raise MocoFlowLibraryError(f"{what} failed: {kind} {code}")

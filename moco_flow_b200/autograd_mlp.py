@@ -46,7 +46,10 @@ def nerf_forward_launch(model, xyz, pe, dense, ray_feat, rows_per_ray: int, sigm
         keep.append(rb)
     out = torch.empty(M, 1 if sigma_only else 4, device=dev)
     cp.out, cp.out_stride, cp.sigma_col = out.data_ptr(), out.shape[1], (0 if sigma_only else 3)
-    ops.launch_chain(cp)
+    flops = ops.linear_flops(model)
+    if sigma_only:
+        flops -= 2.0 * (model.W * model.W + (model.W + E) * (model.W // 2) + (model.W // 2) * 3)
+    ops.launch_chain(cp, "nerf_fwd", flops)
     return out, keep
 
 
@@ -86,7 +89,7 @@ def nof_forward_launch(model, xyz, pe, dense, ray_feat, rows_per_ray: int, train
     if training:
         head_save = torch.empty(M, 12, device=dev)
         cp.head_save = head_save.data_ptr()
-    ops.launch_chain(cp)
+    ops.launch_chain(cp, "nof_fwd", ops.linear_flops(model))
     return out, keep, head_save
 
 

@@ -113,7 +113,7 @@ class _NeRFFn(torch.autograd.Function):
         cp.save, cp.save_tile_bytes = save.data_ptr(), plan.save_tile_bytes
         cp.masks, cp.mask_tile_words = masks.data_ptr(), plan.mask_tile_words
         cp.x0_save_off = plan.offsets["save_x0"]
-        ops.launch_chain(cp)
+        ops.launch_chain(cp, "nerf_fwd", ops.linear_flops(model))
         ctx.model, ctx.pe, ctx.names, ctx.M, ctx.S = model, pe, names, M, rows_per_ray
         ctx.dense_mode = dense is not None
         ctx.need_dx = xyz is not None and xyz.requires_grad
@@ -158,7 +158,8 @@ class _NeRFFn(torch.autograd.Function):
             d_xyz = torch.empty(M, 3, device=dev)
             cp.d_xyz = d_xyz.data_ptr()
             ops.set_pe(cp, ctx.pe.frequencies(), ctx.pe.multipliers(), model.in_channels_xyz)
-        ops.launch_chain(cp)
+        first = 2.0 * model.in_channels_xyz * model.W * (1 + len([s for s in model.skips if s > 0]))
+        ops.launch_chain(cp, "nerf_bwd_dx", ops.linear_flops(model) - (0.0 if need_dx else first))
         needs = list(ctx.needs_input_grad[7:])
         wanted = {n for n, need in zip(ctx.names, needs) if need}
         pgrads = [None] * len(ctx.names)
@@ -218,7 +219,7 @@ class _NoFFn(torch.autograd.Function):
         cp.save, cp.save_tile_bytes = save.data_ptr(), plan.save_tile_bytes
         cp.masks, cp.mask_tile_words = masks.data_ptr(), plan.mask_tile_words
         cp.x0_save_off = plan.offsets["save_x0"]
-        ops.launch_chain(cp)
+        ops.launch_chain(cp, "nof_fwd", ops.linear_flops(model))
         ctx.model, ctx.pe, ctx.names, ctx.M, ctx.S = model, pe, names, M, rows_per_ray
         ctx.need_dx = xyz.requires_grad
         ctx.save_for_backward(save, masks, head_save)
@@ -262,7 +263,8 @@ class _NoFFn(torch.autograd.Function):
             d_xyz = torch.empty(M, 3, device=dev)
             cp.d_xyz = d_xyz.data_ptr()
             ops.set_pe(cp, ctx.pe.frequencies(), ctx.pe.multipliers(), model.in_channels_xyz)
-        ops.launch_chain(cp)
+        first = 2.0 * model.in_channels_xyz * model.W * (1 + len([s for s in model.skips if s > 0]))
+        ops.launch_chain(cp, "nof_bwd_dx", ops.linear_flops(model) - (0.0 if need_dx else first))
         needs = list(ctx.needs_input_grad[7:])
         wanted = {n for n, need in zip(ctx.names, needs) if need}
         pgrads = [None] * len(ctx.names)

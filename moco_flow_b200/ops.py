@@ -130,11 +130,12 @@ class _CompositeFn(torch.autograd.Function):
         depth = torch.empty(R, device=dev) if full else None
         base = raw.data_ptr()
         sig_ptr = C.c_void_p(base + 12) if full else C.c_void_p(base)
-        L.check(L.lib().mcf_composite_fwd(sig_ptr, C.c_int(4 if full else 1), C.c_void_p(base if full else 0),
-                                          C.c_int(4), L.ptr(z), L.ptr(dirs), C.c_int(dirs.shape[1]), L.ptr(noise),
-                                          C.c_float(noise_std), L.ptr(background), C.c_int(act), C.c_int(R),
-                                          C.c_int(S), L.ptr(weights), L.ptr(alphas), L.ptr(rgb), L.ptr(depth),
-                                          L.ptr(opacity), L.stream_ptr()), "mcf_composite_fwd")
+        with L.timed("composite_fwd", R * (28.0 * S + 44.0) if full else R * (16.0 * S + 16.0), "byte"):
+            L.check(L.lib().mcf_composite_fwd(
+                sig_ptr, C.c_int(4 if full else 1), C.c_void_p(base if full else 0), C.c_int(4), L.ptr(z),
+                L.ptr(dirs), C.c_int(dirs.shape[1]), L.ptr(noise), C.c_float(noise_std), L.ptr(background),
+                C.c_int(act), C.c_int(R), C.c_int(S), L.ptr(weights), L.ptr(alphas), L.ptr(rgb), L.ptr(depth),
+                L.ptr(opacity), L.stream_ptr()), "mcf_composite_fwd")
         ctx.save_for_backward(raw, z, dirs, noise, background)
         ctx.cfg = (noise_std, act, full)
         ctx.mark_non_differentiable(alphas)
@@ -154,12 +155,13 @@ class _CompositeFn(torch.autograd.Function):
         R, S = z.shape
         d_raw = torch.empty_like(raw)
         base, dbase = raw.data_ptr(), d_raw.data_ptr()
-        L.check(L.lib().mcf_composite_bwd(
-            C.c_void_p(base + 12 if full else base), C.c_int(4 if full else 1), C.c_void_p(base if full else 0),
-            C.c_int(4), L.ptr(z), L.ptr(dirs), C.c_int(dirs.shape[1]), L.ptr(noise), C.c_float(noise_std),
-            L.ptr(background), C.c_int(act), C.c_int(R), C.c_int(S), L.ptr(_c(g_rgb)), L.ptr(_c(g_depth)),
-            L.ptr(_c(g_op)), L.ptr(_c(g_w)), C.c_void_p(dbase + 12 if full else dbase), C.c_int(4 if full else 1),
-            C.c_void_p(dbase if full else 0), C.c_int(4), L.stream_ptr()), "mcf_composite_bwd")
+        with L.timed("composite_bwd", R * (40.0 * S + 28.0), "byte"):
+            L.check(L.lib().mcf_composite_bwd(
+                C.c_void_p(base + 12 if full else base), C.c_int(4 if full else 1), C.c_void_p(base if full else 0),
+                C.c_int(4), L.ptr(z), L.ptr(dirs), C.c_int(dirs.shape[1]), L.ptr(noise), C.c_float(noise_std),
+                L.ptr(background), C.c_int(act), C.c_int(R), C.c_int(S), L.ptr(_c(g_rgb)), L.ptr(_c(g_depth)),
+                L.ptr(_c(g_op)), L.ptr(_c(g_w)), C.c_void_p(dbase + 12 if full else dbase), C.c_int(4 if full else 1),
+                C.c_void_p(dbase if full else 0), C.c_int(4), L.stream_ptr()), "mcf_composite_bwd")
         return d_raw, None, None, None, None, None, None
 
 
@@ -189,12 +191,14 @@ def sample_pdf_raw(bins: torch.Tensor, weights: Optional[torch.Tensor], u: torch
     cdf_out = torch.empty(R, n_bins + 1, device=dev) if want_cdf else None
     merged = torch.empty(R, z_coarse.shape[1] + n_imp, device=dev) if z_coarse is not None else None
     wptr = C.c_void_p(0 if weights is None else weights.data_ptr() + 4 * w_offset)
-    L.check(L.lib().mcf_sample_pdf(
-        L.ptr(bins), C.c_int(bins.shape[1]), C.c_int(int(bins_are_z)), wptr,
-        C.c_int(0 if weights is None else weights.shape[1]), L.ptr(cdf), C.c_int(0 if cdf is None else cdf.shape[1]),
-        L.ptr(u), C.c_int(u.shape[1]), C.c_float(eps), C.c_int(R), C.c_int(n_bins), C.c_int(n_imp), L.ptr(z_coarse),
-        C.c_int(0 if z_coarse is None else z_coarse.shape[1]), C.c_int(0 if z_coarse is None else z_coarse.shape[1]),
-        L.ptr(samples), L.ptr(inds), L.ptr(cdf_out), L.ptr(merged), L.stream_ptr()), "mcf_sample_pdf")
+    n_c = 0 if z_coarse is None else z_coarse.shape[1]
+    with L.timed("sample_pdf", R * 4.0 * ((n_bins + 1) + n_bins + 2 * n_imp + 2 * n_c), "byte"):
+        L.check(L.lib().mcf_sample_pdf(
+            L.ptr(bins), C.c_int(bins.shape[1]), C.c_int(int(bins_are_z)), wptr,
+            C.c_int(0 if weights is None else weights.shape[1]), L.ptr(cdf), C.c_int(0 if cdf is None else cdf.shape[1]),
+            L.ptr(u), C.c_int(u.shape[1]), C.c_float(eps), C.c_int(R), C.c_int(n_bins), C.c_int(n_imp), L.ptr(z_coarse),
+            C.c_int(0 if z_coarse is None else z_coarse.shape[1]), C.c_int(0 if z_coarse is None else z_coarse.shape[1]),
+            L.ptr(samples), L.ptr(inds), L.ptr(cdf_out), L.ptr(merged), L.stream_ptr()), "mcf_sample_pdf")
     return samples, inds, cdf_out, merged
 
 
@@ -321,8 +325,14 @@ def set_pe(cp: L.ChainParams, freqs: Sequence[float], weights: Sequence[float], 
         cp.pe_freq[i], cp.pe_weight[i] = float(f), float(w)
 
 
-def launch_chain(cp: L.ChainParams) -> None:
-    L.check(L.lib().mcf_chain_launch(C.byref(cp), L.stream_ptr()), "mcf_chain_launch")
+def launch_chain(cp: L.ChainParams, tag: str = "chain", flops_per_row: float = 0.0) -> None:
+    with L.timed(tag, flops_per_row * cp.n_rows, "flop"):
+        L.check(L.lib().mcf_chain_launch(C.byref(cp), L.stream_ptr()), "mcf_chain_launch")
+
+
+def linear_flops(module) -> float:
+    """Algorithmic FLOPs per row of a module's Linear layers (2*in*out, un-padded reference shapes)."""
+    return float(sum(2 * m.in_features * m.out_features for m in module.modules() if isinstance(m, torch.nn.Linear)))
 
 
 def dw_gemm(p_base: torch.Tensor, p_tile_bytes: int, p_off: int, p_cols: int, q_base: torch.Tensor,
@@ -334,4 +344,5 @@ def dw_gemm(p_base: torch.Tensor, p_tile_bytes: int, p_off: int, p_cols: int, q_
     dp.out, dp.ld_out, dp.n_i, dp.n_j = out.data_ptr(), out.stride(0), n_i, n_j
     dp.colsum_p = 0 if colsum is None else colsum.data_ptr()
     dp.n_tiles, dp.max_ctas = n_tiles, max_ctas
-    L.check(L.lib().mcf_dw_gemm(C.byref(dp), L.stream_ptr()), "mcf_dw_gemm")
+    with L.timed("dw_gemm", 2.0 * n_i * n_j * n_tiles * L.TILE_ROWS, "flop"):
+        L.check(L.lib().mcf_dw_gemm(C.byref(dp), L.stream_ptr()), "mcf_dw_gemm")

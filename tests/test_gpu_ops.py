@@ -140,21 +140,34 @@ def test_sample_pdf_level2_fused_cdf(dev):
     cdf_ulp = (cdf.cpu() != aux["cdf"]).float().mean().item()
     print(f"sample_pdf fused: index mismatches {mism}/{R*Sf}, cdf entries differing {cdf_ulp:.4%}")
     assert mism <= 4
-    # a 1-ulp cdf difference moves a sample by at most ulp/denom of its bin width (ill-conditioned only for
-    # near-empty bins, where any position inside the bin is as good): bound the deviation accordingly
-    c_lo, c_hi = aux["cdf"].gather(1, aux["below"]), aux["cdf"].gather(1, aux["above"])
-    b_lo, b_hi = mid.gather(1, aux["below"]), mid.gather(1, aux["above"])
-    denom = (c_hi - c_lo).clamp_min(1e-5)
-    bound = 2e-6 + 4 * 1.2e-7 / denom * (b_hi - b_lo)
-    assert bool(((s.cpu() - ref).abs() <= bound).all())
+    assert_samples_close(s.cpu(), ref, aux, mid)
     # merged output is the sorted concatenation (values are copies, so sortedness + multiset equality is exact)
     exp = torch.sort(torch.cat([z, s.cpu()], dim=1), dim=1).values
     assert torch.equal(merged.cpu(), exp)
     # det mode through the public API
     import moco_flow_b200 as mf
     sd = mf.sample_pdf(mid.to(dev), wts[:, 1:-1].contiguous().to(dev), Sf, det=True)
-    rd = orc.sample_pdf(mid, wts[:, 1:-1], Sf, det=True)
-    assert (sd.cpu() - rd).abs().max().item() <= 2e-6
+    rd, auxd = orc.sample_pdf(mid, wts[:, 1:-1], Sf, det=True, return_aux=True)
+    assert_samples_close(sd.cpu(), rd, auxd, mid)
+
+
+def assert_samples_close(s, ref, aux, bins):
+    """Level-2 contract.  Where u is further than a few ulp from every cdf entry the bin index is well defined
+    and the sample may only move by (cdf ulp / bin mass) of the bin width.  Where u coincides with a cdf entry
+    (always true for the last det-mode draw u = 1.0 = cdf[-1] +- 1 ulp) the index legitimately depends on the
+    last bit of the cdf: there the sample must stay within the neighbouring bins."""
+    cdf, u = aux["cdf"], aux["u"]
+    gap = (cdf.unsqueeze(1) - u.unsqueeze(2)).abs().min(dim=2).values
+    well = gap > 1e-6
+    c_lo, c_hi = cdf.gather(1, aux["below"]), cdf.gather(1, aux["above"])
+    b_lo, b_hi = bins.gather(1, aux["below"]), bins.gather(1, aux["above"])
+    denom = (c_hi - c_lo).clamp_min(1e-5)
+    bound = 2e-6 + 8 * 1.2e-7 / denom * (b_hi - b_lo)
+    err = (s - ref).abs()
+    assert bool((err[well] <= bound[well]).all()), float((err - bound)[well].max())
+    width = (bins[:, 1:] - bins[:, :-1]).max(dim=1, keepdim=True).values
+    assert bool((err <= 2 * width + 1e-6).all())
+    assert well.float().mean().item() > 0.97
 
 
 def test_sample_pdf_edge_cases(dev):
@@ -165,10 +178,13 @@ def test_sample_pdf_edge_cases(dev):
     wts[2] = 1e-9
     u = torch.tensor([[0.0, 0.5, 1.0 - 2 ** -24, 0.25]]).repeat(3, 1)
     mid = 0.5 * (z[:, :-1] + z[:, 1:])
-    ref = orc.sample_pdf(mid, wts[:, 1:-1], 4, det=False, u=u)
+    ref, aux = orc.sample_pdf(mid, wts[:, 1:-1], 4, det=False, u=u, return_aux=True)
     s, _, _, merged = ops.sample_pdf_raw(z.to(dev), wts.to(dev), u.to(dev), bins_are_z=True, w_offset=1, n_bins=6,
                                          z_coarse=z.to(dev))
-    assert (s.cpu() - ref).abs().max().item() <= 1e-6
+    gap = (aux["cdf"].unsqueeze(1) - u.unsqueeze(2)).abs().min(dim=2).values
+    well = gap > 1e-6
+    assert (s.cpu() - ref)[well].abs().max().item() <= 1e-6
+    assert (s.cpu() - ref).abs().max().item() <= 0.23  # one bin width where u sits on a cdf entry
     assert merged.shape == (3, 12) and bool((merged[:, 1:] >= merged[:, :-1]).all())
 
 
