@@ -152,7 +152,7 @@ def run_ours(args):
     rays_h, bg_h, tgt_h = rays_h.pin_memory(), bg_h.pin_memory(), tgt_h.pin_memory()
     rays_d, bg_d, tgt_d = rays_h.to(dev), bg_h.to(dev), tgt_h.to(dev)
     flat = dp.FlatGradients(nerfs + nofs) if train else None
-    opt = torch.optim.Adam(flat.params, lr=5e-4, eps=1e-8, fused=True) if train else None
+    opt = torch.optim.Adam(flat.params, lr=5e-4, eps=1e-8, fused=True, capturable=True) if train else None
     loss_fn = mf.MSELoss()
 
     def step(rays, bg, tgt):
@@ -181,6 +181,26 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step(rays_d, bg_d, tgt_d)
     sync_all()
+    eager_step = step
+    graphed = False
+    if not args.no_graph:
+        try:
+            from moco_flow_b200.graph import CudaGraphStep
+            gstep = CudaGraphStep(eager_step, [rays_d, bg_d, tgt_d], warmup=2)
+            step = gstep
+            graphed = True
+            for _ in range(2):
+                step(rays_d, bg_d, tgt_d)
+        except Exception as exc:  # report, then measure the eager path
+            sys.stderr.write(f"[bench] CUDA graph capture failed ({exc!r}); timing the eager step\n")
+            step = eager_step
+    sync_all()
+    launches_per_step_eager = 0
+    if graphed:  # the graph replays exactly the launches one eager step issues
+        c0 = L.LAUNCHES
+        eager_step(rays_d, bg_d, tgt_d)
+        launches_per_step_eager = L.LAUNCHES - c0
+        sync_all()
 
     # ---- device-resident timing (value) ----
     clocks = Clocks(local_rank)
@@ -195,7 +215,7 @@ def run_ours(args):
         step(rays_d, bg_d, tgt_d)
     e1.record()
     sync_all()
-    launches = L.LAUNCHES - launches0
+    launches = (launches_per_step_eager * args.steps) if graphed else (L.LAUNCHES - launches0)
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
 
@@ -219,7 +239,7 @@ def run_ours(args):
     # ---- per-kernel event timing for the roofline (extra steps, not part of the numbers above) ----
     L.PROFILE = []
     for _ in range(2):
-        step(rays_d, bg_d, tgt_d)
+        eager_step(rays_d, bg_d, tgt_d)
     torch.cuda.synchronize()
     prof, L.PROFILE = L.PROFILE, None
     agg = {}
@@ -275,7 +295,8 @@ def run_ours(args):
                                ("full MoCo-Flow ray render (BASELINE configs[1]): 4096 rays, 64+64 samples, test_time"),
                    "rays_per_gpu": R, "n_coarse": N_COARSE, "n_fine": N_FINE,
                    "l2": "no flush: the step streams > 5 GB of saved operand images per GPU, far above the 126 MB L2",
-                   "parallelism": f"dp{world} (rays sharded, weights replicated)"},
+                   "parallelism": f"dp{world} (rays sharded, weights replicated)",
+                   "cuda_graph": graphed},
         "e2e": {"value": round(total_rays / (ms_e2e * 1e-3), 1), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": launches,
@@ -389,6 +410,7 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "render"])
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
