@@ -86,6 +86,38 @@ __device__ __forceinline__ void load32f(const float* __restrict__ p, float (&b)[
   }
 }
 
+// Bias (+ReLU) epilogue for 32 accumulator columns: packed fp32x2 adds, ReLU fused into the bf16x2 convert,
+// sign bits funnel-shifted into the ReLU bit mask (bit j set <=> column j is active).
+template <bool kRelu, bool kMask>
+__device__ __forceinline__ uint32_t bias_act_store32(uint8_t* hbuf, uint32_t row, uint32_t col0, uint32_t (&v)[32],
+                                                     const float (&b)[32]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) add_f32x2(v[2 * j], v[2 * j + 1], b[2 * j], b[2 * j + 1]);
+  uint32_t word = 0;
+  if (kMask) {
+#pragma unroll
+    for (int j = 31; j >= 0; --j) word = __funnelshift_l(v[j], word, 1);  // collects sign bits, bit j <- v[j]
+    word = ~word;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 o;
+    if (kRelu) {
+      o.x = cvt_bf16x2_relu_bits(v[q * 8 + 0], v[q * 8 + 1]);
+      o.y = cvt_bf16x2_relu_bits(v[q * 8 + 2], v[q * 8 + 3]);
+      o.z = cvt_bf16x2_relu_bits(v[q * 8 + 4], v[q * 8 + 5]);
+      o.w = cvt_bf16x2_relu_bits(v[q * 8 + 6], v[q * 8 + 7]);
+    } else {
+      o.x = cvt_bf16x2_bits(v[q * 8 + 0], v[q * 8 + 1]);
+      o.y = cvt_bf16x2_bits(v[q * 8 + 2], v[q * 8 + 3]);
+      o.z = cvt_bf16x2_bits(v[q * 8 + 4], v[q * 8 + 5]);
+      o.w = cvt_bf16x2_bits(v[q * 8 + 6], v[q * 8 + 7]);
+    }
+    store_h8(hbuf, row, col0 + q * 8, o);
+  }
+  return word;
+}
+
 struct RowState {   // per-thread state that lives across the rounds of one tile
   float sigma;      // fwd: sigma head value; bwd: d_sigma
   float dx[3];      // bwd: accumulated d_xyz
@@ -451,30 +483,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         const float* bias_p = (rd.raybias >= 0) ? (p.raybias[rd.raybias] + ray * rd.n_out) : (p.consts + rd.const_off);
 
         if (rd.epi == MCF_EPI_RELU || rd.epi == MCF_EPI_RELU_SIGMA || rd.epi == MCF_EPI_LINEAR) {
+          const bool want_mask = p.masks != nullptr && rd.mask_off != kNone;
+          uint32_t* mk = want_mask ? (p.masks + tile * p.mask_tile_words + rd.mask_off + row) : nullptr;
           float sig = 0.f;
           for (int c0 = 0; c0 < rd.n_out; c0 += 32) {
             uint32_t v[32];
-            float f[32], b[32];
+            float b[32];
             tmem_ld32(t_acc + c0, v);
             load32f(bias_p + c0, b);
             tmem_ld_wait();
-            uint32_t word = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float t = __uint_as_float(v[j]) + b[j];
-              if (rd.epi != MCF_EPI_LINEAR) t = fmaxf(t, 0.f);
-              word |= (t > 0.f ? 1u : 0u) << j;
-              f[j] = t;
-            }
-            if (rd.epi == MCF_EPI_RELU_SIGMA) {
+            if (rd.epi == MCF_EPI_LINEAR) {
+              bias_act_store32<false, false>(hbuf, row, c0, v, b);
+            } else if (rd.epi == MCF_EPI_RELU_SIGMA) {
               float ws[32];
               load32f(p.consts + rd.aux_off + c0, ws);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) sig = fmaf(f[j], ws[j], sig);
+              for (int j = 0; j < 32; ++j) sig = fmaf(fmaxf(__uint_as_float(v[j]) + b[j], 0.f), ws[j], sig);
+              const uint32_t word = bias_act_store32<true, true>(hbuf, row, c0, v, b);
+              if (want_mask) mk[(c0 >> 5) * 128] = word;
+            } else if (want_mask) {
+              mk[(c0 >> 5) * 128] = bias_act_store32<true, true>(hbuf, row, c0, v, b);
+            } else {
+              bias_act_store32<true, false>(hbuf, row, c0, v, b);
             }
-            store_h32(hbuf, row, c0, f);
-            if (p.masks && rd.mask_off != kNone)
-              p.masks[tile * p.mask_tile_words + rd.mask_off + (c0 >> 5) * 128 + row] = word;
           }
           if (rd.epi == MCF_EPI_RELU_SIGMA) {
             st.sigma = sig + __ldg(p.consts + rd.aux_off + rd.n_out);

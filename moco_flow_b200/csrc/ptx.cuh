@@ -182,6 +182,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
+// packed fp32x2 add (sm_100 FADD2): {a0,a1} += {b0,b1}; operands are the raw bit patterns of the accumulators
+__device__ __forceinline__ void add_f32x2(uint32_t& a0, uint32_t& a1, float b0, float b1) {
+  uint64_t a, b, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "l"(d));
+}
+// two fp32 (bit patterns) -> packed bf16x2 (lo in the low half), optionally fused with ReLU
+__device__ __forceinline__ uint32_t cvt_bf16x2_bits(uint32_t lo, uint32_t hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2_relu_bits(uint32_t lo, uint32_t hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return d;
+}
+
 // byte offset of 16-byte chunk `c16` (0..7) of row `r` inside one [rows][64 bf16] 128B-swizzled block
 __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t c16) {
   return r * 128u + (((c16 ^ (r & 7u)) & 7u) << 4);
