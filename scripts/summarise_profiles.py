@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Condense gpurun_out/ ncu exports into small tracked files under profiles/ (per round).
 
-    python scripts/summarise_profiles.py r01
+    python scripts/summarise_profiles.py <suffix used on the GPU box> [<prefix under profiles/>]
 """
 import collections
 import csv
@@ -77,14 +77,15 @@ def full(path, tag, rnd):
 
 
 def main():
-    rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    src = sys.argv[1] if len(sys.argv) > 1 else "r01"   # suffix used by scripts/gpu_profile.sh
+    rnd = sys.argv[2] if len(sys.argv) > 2 else src     # prefix of the files written under profiles/
     os.makedirs(DST, exist_ok=True)
     for tag in ("train", "render"):
-        p = os.path.join(OUT, f"launches_{tag}_{rnd}.csv")
+        p = os.path.join(OUT, f"launches_{tag}_{src}.csv")
         if os.path.exists(p):
             launch_list(p, tag, rnd)
     for tag in ("chain_render", "chain_train", "dw", "render_ops"):
-        p = os.path.join(OUT, f"prof_{tag}_{rnd}_raw.csv")
+        p = os.path.join(OUT, f"prof_{tag}_{src}_raw.csv")
         if os.path.exists(p):
             full(p, tag, rnd)
     for name in ("bench_train.json", "bench_render.json"):
