@@ -282,11 +282,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             tc_fence_after();
             for (int c = cb; c < ce; ++c) {
               mbar_wait(&tab.w_full[stage], phase, 0x300u | stage);
-              tc_fence_after();
               const mcf_chunk_t ch = tab.chunks[c];
+              // flag bit1: this chunk and the next one are the two 128-row halves of one [256 x 64] weight tile
+              // sitting in consecutive (even, odd) ring stages -> one N=256 instruction per K step
+              const bool fuse = (ch.flags & 2u) != 0u;
+              if (fuse) mbar_wait(&tab.w_full[stage + 1], phase, 0x300u | (stage + 1));
+              tc_fence_after();
               const uint32_t a_base = (ch.a_buf ? (h_addr + s * L::kHBytes) : (x0_addr + s * kBlk)) + ch.a_kblock * kBlk;
               const uint32_t b_base = ring_addr + stage * kBlk;
-              const uint32_t idesc = make_idesc(ch.n);
+              const uint32_t idesc = make_idesc(fuse ? 2u * ch.n : (uint32_t)ch.n);
               const uint32_t d_tmem = tmem_base + s * kSlotCols + ch.acc_col;
               for (uint32_t k = 0; k < ch.ksteps; ++k) {
                 const uint64_t ad = make_sdesc(a_base + k * 32u, 0u, 1024u);
@@ -295,6 +299,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
               }
               umma_commit(&tab.w_empty[stage]);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              if (fuse) {
+                umma_commit(&tab.w_empty[stage]);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                ++c;
+              }
             }
             umma_commit(&tab.acc_full[s]);
           }
@@ -469,6 +478,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       // ------------------------------- rounds -------------------------------
       for (int r = 0; r < p.n_rounds; ++r) {
         const mcf_round_t rd = tab.rounds[r];
+        const float* bias_p = (rd.raybias >= 0) ? (p.raybias[rd.raybias] + ray * rd.n_out) : (p.consts + rd.const_off);
+        const bool is_bias_epi = rd.epi == MCF_EPI_RELU || rd.epi == MCF_EPI_RELU_SIGMA || rd.epi == MCF_EPI_LINEAR;
+        const bool is_mask_epi = rd.epi == MCF_EPI_B_MASK || rd.epi == MCF_EPI_B_MASK_SIGMA;
+        // operands that do not depend on the accumulator are fetched before waiting for the tensor core
+        float b0[32];
+        uint32_t mwords[8];
+        if (is_bias_epi) load32f(bias_p, b0);
+        if (is_mask_epi && rd.mask_off != kNone) {
+          const uint32_t* mkp = p.fwd_masks + tile * p.fwd_mask_tile_words + rd.mask_off + row;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mwords[j] = (j * 32 < rd.n_out) ? __ldg(mkp + j * 128) : 0u;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mwords[j] = 0xFFFFFFFFu;
+        }
         mbar_wait(&tab.acc_full[s], af_phase, 0x400u | s);
         af_phase ^= 1u;
         tc_fence_after();
@@ -480,18 +504,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           store_pending = false;
         }
         const uint32_t t_acc = t_row + rd.acc_col;
-        const float* bias_p = (rd.raybias >= 0) ? (p.raybias[rd.raybias] + ray * rd.n_out) : (p.consts + rd.const_off);
 
         if (rd.epi == MCF_EPI_RELU || rd.epi == MCF_EPI_RELU_SIGMA || rd.epi == MCF_EPI_LINEAR) {
           const bool want_mask = p.masks != nullptr && rd.mask_off != kNone;
           uint32_t* mk = want_mask ? (p.masks + tile * p.mask_tile_words + rd.mask_off + row) : nullptr;
           float sig = 0.f;
-          for (int c0 = 0; c0 < rd.n_out; c0 += 32) {
-            uint32_t v[32];
-            float b[32];
-            tmem_ld32(t_acc + c0, v);
-            load32f(bias_p + c0, b);
-            tmem_ld_wait();
+          float b1[32];
+          auto do_chunk = [&](int c0, uint32_t (&v)[32], const float (&b)[32]) {
             if (rd.epi == MCF_EPI_LINEAR) {
               bias_act_store32<false, false>(hbuf, row, c0, v, b);
             } else if (rd.epi == MCF_EPI_RELU_SIGMA) {
@@ -506,6 +525,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             } else {
               bias_act_store32<true, false>(hbuf, row, c0, v, b);
             }
+          };
+          for (int c0 = 0; c0 < rd.n_out; c0 += 64) {  // n_out is a multiple of 64 for these rounds
+            uint32_t v[32];
+            tmem_ld32(t_acc + c0, v);
+            load32f(bias_p + c0 + 32, b1);
+            tmem_ld_wait();
+            do_chunk(c0, v, b0);
+            tmem_ld32(t_acc + c0 + 32, v);
+            if (c0 + 64 < rd.n_out) load32f(bias_p + c0 + 64, b0);
+            tmem_ld_wait();
+            do_chunk(c0 + 32, v, b1);
           }
           if (rd.epi == MCF_EPI_RELU_SIGMA) {
             st.sigma = sig + __ldg(p.consts + rd.aux_off + rd.n_out);
@@ -572,13 +602,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             }
           }
         } else if (rd.epi == MCF_EPI_B_MASK || rd.epi == MCF_EPI_B_MASK_SIGMA || rd.epi == MCF_EPI_B_LINEAR) {
-          const uint32_t* mk = (rd.epi != MCF_EPI_B_LINEAR && rd.mask_off != kNone)
-                                   ? (p.fwd_masks + tile * p.fwd_mask_tile_words + rd.mask_off) : nullptr;
           for (int c0 = 0; c0 < rd.n_out; c0 += 32) {
             uint32_t v[32];
             float f[32];
             tmem_ld32(t_acc + c0, v);
-            const uint32_t word = mk ? mk[(c0 >> 5) * 128 + row] : 0xFFFFFFFFu;
+            uint32_t word = 0xFFFFFFFFu;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j == (c0 >> 5)) word = mwords[j];
             tmem_ld_wait();
             if (rd.epi == MCF_EPI_B_MASK_SIGMA) {
               float ws[32];
@@ -699,7 +730,7 @@ __global__ void k_unpack(const mcf_unpack_t* __restrict__ table, const float* __
                          float* __restrict__ grads) {
   const mcf_unpack_t e = table[blockIdx.x];
   const int n = e.nrows * e.ncols;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     const int r = i / e.ncols, c = i - r * e.ncols;
     const float v = e.transposed ? staging[e.src_off + (long long)c * e.src_ld + r]
                                  : staging[e.src_off + (long long)r * e.src_ld + c];
@@ -707,23 +738,22 @@ __global__ void k_unpack(const mcf_unpack_t* __restrict__ table, const float* __
   }
 }
 
-__global__ void k_colsum(const float* __restrict__ src, long long n_rows, int stride, int ncols,
+// Column sums of a row-major [n_rows][stride] fp32 array (first ncols columns).  The array is walked as a flat,
+// fully coalesced stream; each thread keeps the running sum of the single column its flat indices map to
+// (blockDim * gridDim is a multiple of stride, so that column never changes), then shared-memory + global atomics.
+__global__ void k_colsum(const float* __restrict__ src, long long n_elems, int stride, int ncols,
                          float* __restrict__ out) {
-  float acc[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < n_rows;
-       m += (long long)gridDim.x * blockDim.x) {
-#pragma unroll
-    for (int c = 0; c < 16; ++c)
-      if (c < ncols) acc[c] += src[m * stride + c];
-  }
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    float v = acc[c];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && c < ncols) atomicAdd(out + c, v);
-  }
+  __shared__ float bins[16];
+  if (threadIdx.x < 16) bins[threadIdx.x] = 0.f;
+  __syncthreads();
+  const long long step = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int col = (int)(i % stride);
+  float acc = 0.f;
+  for (; i < n_elems; i += step) acc += src[i];
+  if (col < ncols) atomicAdd(&bins[col], acc);
+  __syncthreads();
+  if (threadIdx.x < ncols) atomicAdd(out + threadIdx.x, bins[threadIdx.x]);
 }
 
 }  // namespace mcf
@@ -733,17 +763,22 @@ extern "C" {
 int mcf_unpack(const mcf_unpack_t* table_dev, int n_entries, const float* staging, float* grads,
                cudaStream_t stream) {
   if (n_entries <= 0) return 0;
-  mcf::k_unpack<<<n_entries, 256, 0, stream>>>(table_dev, staging, grads);
+  mcf::k_unpack<<<dim3(n_entries, 16), 256, 0, stream>>>(table_dev, staging, grads);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
 
 int mcf_colsum(const float* src, long long n_rows, int stride, int ncols, float* out, cudaStream_t stream) {
   if (n_rows <= 0) return 0;
-  if (ncols < 1 || ncols > 16) return MCF_ERR_BAD_ARG;
-  long long blocks = (n_rows + 255) / 256;
-  if (blocks > 592) blocks = 592;
-  mcf::k_colsum<<<(unsigned)blocks, 256, 0, stream>>>(src, n_rows, stride, ncols, out);
+  if (ncols < 1 || ncols > 16 || stride < ncols || stride > 16) return MCF_ERR_BAD_ARG;
+  // 192 threads = lcm-friendly for strides 4 and 12; grid*block must be a multiple of stride
+  const int threads = 192;
+  if ((threads % stride) != 0) return MCF_ERR_UNSUPPORTED;
+  long long n_elems = n_rows * stride;
+  long long blocks = (n_elems + threads * 8 - 1) / (threads * 8);
+  if (blocks > 1184) blocks = 1184;
+  if (blocks < 1) blocks = 1;
+  mcf::k_colsum<<<(unsigned)blocks, threads, 0, stream>>>(src, n_elems, stride, ncols, out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

@@ -121,17 +121,33 @@ __global__ void k_pe_bwd(const float* __restrict__ x, const float* __restrict__ 
 // per-ray bias:  out[r, n] = bias[n] + sum_j W[n, col_off + j] * feat[r, j]      (fp32, exact fold of
 // the per-ray constant input columns -- index / direction embeddings -- of a Linear layer)
 // -------------------------------------------------------------------------------------------------
-__global__ void k_ray_bias(const float* __restrict__ W, int w_stride, int col_off, const float* __restrict__ bias,
-                           const float* __restrict__ feat, int feat_stride, int E, int R, int N,
-                           float* __restrict__ out) {
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= (long long)R * N) return;
-  int r = static_cast<int>(idx / N), n = static_cast<int>(idx - (long long)r * N);
-  const float* w = W + (long long)n * w_stride + col_off;
-  const float* f = feat + (long long)r * feat_stride;
-  float acc = bias ? bias[n] : 0.0f;
-  for (int j = 0; j < E; ++j) acc = fmaf(w[j], f[j], acc);
-  out[idx] = acc;
+// One block = 32 rays x all N outputs; the [N x E] weight slice is staged (transposed) in shared memory so that
+// both the weight reads and the output writes are coalesced.
+constexpr int kRbRays = 32;
+__global__ void __launch_bounds__(256)
+k_ray_bias(const float* __restrict__ W, int w_stride, int col_off, const float* __restrict__ bias,
+           const float* __restrict__ feat, int feat_stride, int E, int R, int N, float* __restrict__ out) {
+  extern __shared__ float sh[];
+  float* sW = sh;                 // [E][N]  (transposed slice)
+  float* sF = sh + (size_t)E * N; // [kRbRays][E]
+  for (int i = threadIdx.x; i < N * E; i += blockDim.x) {
+    int n = i / E, j = i - n * E;
+    sW[j * N + n] = W[(long long)n * w_stride + col_off + j];
+  }
+  const int r0 = blockIdx.x * kRbRays;
+  for (int i = threadIdx.x; i < kRbRays * E; i += blockDim.x) {
+    int rr = i / E, j = i - rr * E;
+    sF[i] = (r0 + rr < R) ? feat[(long long)(r0 + rr) * feat_stride + j] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kRbRays * N; i += blockDim.x) {
+    int rr = i / N, n = i - rr * N;
+    if (r0 + rr >= R) break;
+    float acc = bias ? bias[n] : 0.0f;
+    const float* f = sF + rr * E;
+    for (int j = 0; j < E; ++j) acc = fmaf(sW[j * N + n], f[j], acc);
+    out[(long long)(r0 + rr) * N + n] = acc;
+  }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -579,9 +595,14 @@ int mcf_pe_bwd(const float* x, const float* dy, long long n_rows, int in_channel
 int mcf_ray_bias(const float* W, int w_stride, int col_off, const float* bias, const float* feat, int feat_stride,
                  int n_feat, int n_rays, int n_out, float* out, cudaStream_t stream) {
   if (n_rays <= 0 || n_out <= 0) return 0;
-  long long n = (long long)n_rays * n_out;
-  k_ray_bias<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(W, w_stride, col_off, bias, feat, feat_stride, n_feat,
-                                                             n_rays, n_out, out);
+  size_t smem = ((size_t)n_feat * n_out + (size_t)kRbRays * n_feat) * sizeof(float);
+  if (smem > 160 * 1024) return MCF_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_ray_bias, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k_ray_bias<<<(n_rays + kRbRays - 1) / kRbRays, 256, smem, stream>>>(W, w_stride, col_off, bias, feat, feat_stride,
+                                                                      n_feat, n_rays, n_out, out);
   return check_launch();
 }
 

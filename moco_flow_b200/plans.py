@@ -12,6 +12,7 @@ Shapes follow models/nerf.py:28-59 and models/nof.py:40-53 of the reference.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
@@ -20,6 +21,7 @@ import numpy as np
 from . import _lib as L
 
 BLK = L.BLOCK_BYTES
+FUSE_N256 = os.environ.get("MCF_FUSE_N256", "1") != "0"
 
 
 def _ceil(a: int, b: int) -> int:
@@ -79,7 +81,15 @@ class _Builder:
 
     def chunk(self, img: tuple, a_buf: int, a_kblock: int, ksteps: int, n: int, acc_col: int, init: bool) -> None:
         assert 1 <= ksteps <= 4 and n % 16 == 0 and 16 <= n <= 256
-        self.chunks.append((img[0], img[1], a_buf, a_kblock, ksteps, 1 if init else 0, n, acc_col))
+        self.chunks.append([img[0], img[1], a_buf, a_kblock, ksteps, 1 if init else 0, n, acc_col])
+        # Two consecutive 128-row halves of the same [256 x 64] weight tile landing in an (even, odd) pair of ring
+        # stages are one contiguous 32 KB K-major tile: mark the first so the kernel issues N=256 instructions
+        # (halves the A-operand shared-memory reads per FLOP).
+        if FUSE_N256 and len(self.chunks) >= 2 and len(self.chunks) % 2 == 0:
+            a, b = self.chunks[-2], self.chunks[-1]
+            if (a[2], a[3], a[4], a[5] & 1, a[6]) == (b[2], b[3], b[4], b[5] & 1, b[6]) and a[6] == 128 \
+                    and a[1] == BLK and b[1] == BLK and b[7] == a[7] + 128 and b[0] == a[0] + BLK:
+                a[5] |= 2
 
     def round(self, epi: int, n_out: int, acc_col: int, chunk_begin: int, raybias: int = -1, const_off: int = 0,
               aux_off: int = 0, save_off: int = L.NONE, mask_off: int = L.NONE) -> None:
@@ -99,6 +109,7 @@ class _Builder:
         return off
 
     def finish(self, n_raybias: int = 0) -> Plan:
+        self.chunks = [tuple(c) for c in self.chunks]
         assert len(self.chunks) <= 128 and len(self.rounds) <= 24 and len(self.names) <= 32, \
             (len(self.chunks), len(self.rounds), len(self.names))
         return Plan(self.width, list(self.names),
