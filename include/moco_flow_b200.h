@@ -199,6 +199,10 @@ typedef struct {
   uint32_t extra_save_off; /* 0xFFFFFFFF none                                */
   uint32_t dhead_save_off; /* backward: image block of the head gradients    */
   int32_t max_ctas;        /* 0 = one CTA per SM                             */
+  /* optional instrumentation: [n_ctas][16] cycle counters (NULL = off):
+   * 0-3 slot0 {prologue, wait acc_full, epilogue, save/barrier}, 4-7 slot1, 8 MMA wait act_ready,
+   * 9 MMA wait weights, 10 MMA issue, 11 producer wait ring, 12 total */
+  unsigned long long* timing;
 } mcf_chain_params_t;
 
 int mcf_chain_launch(const mcf_chain_params_t* params_host, cudaStream_t stream);

@@ -197,9 +197,16 @@ __device__ __forceinline__ void nof_quat_backward(const float* h9, const float* 
 // ---------------------------------------------------------------------------------------------
 // the chain kernel
 // ---------------------------------------------------------------------------------------------
+#define MCF_T0(var) long long var = timing ? clock64() : 0
+#define MCF_TACC(slot, var) \
+  do { if (timing) { long long _n = clock64(); tacc[slot] += (unsigned long long)(_n - var); var = _n; } } while (0)
+
 template <int W>
 __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ mcf_chain_params_t p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const bool timing = p.timing != nullptr;
+  unsigned long long tacc[4] = {0ull, 0ull, 0ull, 0ull};
+  const long long t_kernel0 = timing ? clock64() : 0;
   using L = Smem<W>;
   Tables& tab = *reinterpret_cast<Tables*>(smem + L::off_tab);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -255,7 +262,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           for (int s = 0; s < 2; ++s) {
             if (2 * pair + s >= n_tiles) continue;
             for (int c = cb; c < ce; ++c) {
+              MCF_T0(tw);
               mbar_wait(&tab.w_empty[stage], phase ^ 1u, 0x100u | stage);
+              MCF_TACC(0, tw);
               const uint32_t bytes = tab.chunks[c].bytes;
               mbar_arrive_expect_tx(&tab.w_full[stage], bytes);
               bulk_g2s(smem + L::off_ring + stage * kBlk, wsrc + tab.chunks[c].src_off, bytes, &tab.w_full[stage]);
@@ -264,6 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           }
         }
       }
+      if (timing) p.timing[blockIdx.x * 16 + 11] = tacc[0];
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
@@ -277,9 +287,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           const int cb = tab.rounds[r].chunk_begin, ce = tab.rounds[r].chunk_end;
           for (int s = 0; s < 2; ++s) {
             if (2 * pair + s >= n_tiles) continue;
+            MCF_T0(tm);
             mbar_wait(&tab.act_ready[s], ar_phase[s], 0x200u | s);
             ar_phase[s] ^= 1u;
             tc_fence_after();
+            MCF_TACC(0, tm);
             for (int c = cb; c < ce; ++c) {
               mbar_wait(&tab.w_full[stage], phase, 0x300u | stage);
               const mcf_chunk_t ch = tab.chunks[c];
@@ -288,6 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
               const bool fuse = (ch.flags & 2u) != 0u;
               if (fuse) mbar_wait(&tab.w_full[stage + 1], phase, 0x300u | (stage + 1));
               tc_fence_after();
+              MCF_TACC(1, tm);
               const uint32_t a_base = (ch.a_buf ? (h_addr + s * L::kHBytes) : (x0_addr + s * kBlk)) + ch.a_kblock * kBlk;
               const uint32_t b_base = ring_addr + stage * kBlk;
               const uint32_t idesc = make_idesc(fuse ? 2u * ch.n : (uint32_t)ch.n);
@@ -304,10 +317,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 ++c;
               }
+              MCF_TACC(2, tm);
             }
             umma_commit(&tab.acc_full[s]);
           }
         }
+      }
+      if (timing) {
+        p.timing[blockIdx.x * 16 + 8] = tacc[0];
+        p.timing[blockIdx.x * 16 + 9] = tacc[1];
+        p.timing[blockIdx.x * 16 + 10] = tacc[2];
       }
     }
   } else if (warp >= 4) {
@@ -335,6 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       st.sigma = 0.f; st.dx[0] = st.dx[1] = st.dx[2] = 0.f;
       st.aux[0] = st.aux[1] = st.aux[2] = st.aux[3] = 0.f;
 
+      MCF_T0(te);
       // make sure an earlier bulk store no longer reads the buffers we are about to overwrite
       if (store_pending) {
         if (gtid == 0) bulk_wait_read_all();
@@ -474,6 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         store_pending = true;
       }
       mbar_arrive(&tab.act_ready[s]);
+      MCF_TACC(0, te);
 
       // ------------------------------- rounds -------------------------------
       for (int r = 0; r < p.n_rounds; ++r) {
@@ -493,9 +514,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
 #pragma unroll
           for (int j = 0; j < 8; ++j) mwords[j] = 0xFFFFFFFFu;
         }
+        MCF_TACC(2, te);
         mbar_wait(&tab.acc_full[s], af_phase, 0x400u | s);
         af_phase ^= 1u;
         tc_fence_after();
+        MCF_TACC(1, te);
         const bool writes_h = rd.epi != MCF_EPI_NOF_HEAD && rd.epi != MCF_EPI_B_DPE &&
                               !(rd.epi == MCF_EPI_NERF_RGB && !saving);
         if (writes_h && store_pending) {
@@ -662,6 +685,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         }
 
         tc_fence_before();
+        MCF_TACC(2, te);
         if (writes_h) {
           fence_proxy_async_smem();
           if (saving && rd.save_off != kNone) {
@@ -674,14 +698,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           }
         }
         if (r + 1 < p.n_rounds) mbar_arrive(&tab.act_ready[s]);
+        MCF_TACC(3, te);
       }
     }
     if (gtid == 0) bulk_wait_all();
+    if (timing && gtid == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) p.timing[blockIdx.x * 16 + s * 4 + j] = tacc[j];
+    }
   }
 
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
+  if (timing && threadIdx.x == 0) p.timing[blockIdx.x * 16 + 12] = (unsigned long long)(clock64() - t_kernel0);
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 

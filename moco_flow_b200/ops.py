@@ -325,9 +325,18 @@ def set_pe(cp: L.ChainParams, freqs: Sequence[float], weights: Sequence[float], 
         cp.pe_freq[i], cp.pe_weight[i] = float(f), float(w)
 
 
+TIMING = None  # when a dict: tag -> list of [n_ctas][16] in-kernel cycle-counter tensors (scripts/chain_timing.py)
+
+
 def launch_chain(cp: L.ChainParams, tag: str = "chain", flops_per_row: float = 0.0) -> None:
+    buf = None
+    if TIMING is not None:
+        buf = torch.zeros(256, 16, dtype=torch.int64, device="cuda")
+        cp.timing = buf.data_ptr()
     with L.timed(tag, flops_per_row * cp.n_rows, "flop"):
         L.check(L.lib().mcf_chain_launch(C.byref(cp), L.stream_ptr()), "mcf_chain_launch")
+    if buf is not None:
+        TIMING.setdefault(tag, []).append(buf)
 
 
 def linear_flops(module) -> float:
