@@ -251,6 +251,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
   const long long n_tiles = (p.n_rows + MCF_TILE_ROWS - 1) / MCF_TILE_ROWS;
   const long long n_pairs = (n_tiles + 1) / 2;
 
+  // register re-distribution between the warpgroups: the producer/MMA/allocator warpgroup needs few registers,
+  // the two epilogue warpgroups hold 64 accumulator + 64 bias values in flight (128*72 + 256*208 <= 64K)
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
   if (warp == 0) {
     // =========================== weight producer ===========================
     if (lane == 0) {
@@ -329,7 +333,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         p.timing[blockIdx.x * 16 + 10] = tacc[2];
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");
     // =========================== epilogue groups ===========================
     const int s = (warp - 4) >> 2;          // slot
     const int qtr = warp & 3;               // TMEM lane quarter this warp may access
@@ -366,22 +372,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       if (p.prologue == MCF_PRO_PE_XYZ) {
         float x[3] = {0.f, 0.f, 0.f};
         if (valid) { x[0] = p.xyz[m * 3 + 0]; x[1] = p.xyz[m * 3 + 1]; x[2] = p.xyz[m * 3 + 2]; }
-        __nv_bfloat16* xr = reinterpret_cast<__nv_bfloat16*>(x0buf);
-        auto put = [&](int ch, float v) {
-          uint32_t off = sw128_off(row, (uint32_t)ch >> 3) + ((uint32_t)ch & 7u) * 2u;
-          *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(xr) + off) = __float2bfloat16_rn(v);
-        };
+        // channel order of models/embedding.py:42-46: [x | w0 sin(f0 x) | w0 cos(f0 x) | w1 sin(f1 x) | ...]
+        float ch[64];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) put(c, x[c]);
-        for (int k = 0; k < p.pe_n_freqs; ++k) {
-          const float f = p.pe_freq[k], w = p.pe_weight[k];
+        for (int c = 0; c < 64; ++c) ch[c] = 0.f;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float sn, cs;
-            sincosf(f * x[c], &sn, &cs);
-            put(3 + 6 * k + c, w * sn);
-            put(3 + 6 * k + 3 + c, w * cs);
+        for (int c = 0; c < 3; ++c) ch[c] = x[c];
+        float sn[3] = {0.f, 0.f, 0.f}, cs[3] = {1.f, 1.f, 1.f};
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          if (k < p.pe_n_freqs) {
+            const float f = p.pe_freq[k], w = p.pe_weight[k];
+            // full-range sincosf at every 4th octave; in between sin/cos(2a) from sin/cos(a) (<= 3 doublings,
+            // error <= ~8 ulp, far below the bf16 rounding of the operand); non-octave tables stay exact
+            const bool exact = (k & 3) == 0 || f != 2.0f * p.pe_freq[k > 0 ? k - 1 : 0];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              if (exact) {
+                sincosf(f * x[c], &sn[c], &cs[c]);
+              } else {
+                const float s2 = 2.0f * sn[c] * cs[c];
+                const float c2 = fmaf(-2.0f * sn[c], sn[c], 1.0f);
+                sn[c] = s2;
+                cs[c] = c2;
+              }
+              ch[3 + 6 * k + c] = w * sn[c];
+              ch[3 + 6 * k + 3 + c] = w * cs[c];
+            }
           }
+        }
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint4 v;
+          v.x = pack_bf16x2(ch[c8 * 8 + 0], ch[c8 * 8 + 1]); v.y = pack_bf16x2(ch[c8 * 8 + 2], ch[c8 * 8 + 3]);
+          v.z = pack_bf16x2(ch[c8 * 8 + 4], ch[c8 * 8 + 5]); v.w = pack_bf16x2(ch[c8 * 8 + 6], ch[c8 * 8 + 7]);
+          *reinterpret_cast<uint4*>(x0buf + sw128_off(row, c8)) = v;
         }
       } else if (p.prologue == MCF_PRO_DENSE) {
         const float* src = p.dense + mc * p.dense_stride;
@@ -549,16 +574,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
               bias_act_store32<true, false>(hbuf, row, c0, v, b);
             }
           };
-          for (int c0 = 0; c0 < rd.n_out; c0 += 64) {  // n_out is a multiple of 64 for these rounds
-            uint32_t v[32];
-            tmem_ld32(t_acc + c0, v);
+          // TMEM loads run one 32-column chunk ahead of the math (n_out is a multiple of 64 for these rounds)
+          uint32_t va[32], vb[32];
+          tmem_ld32(t_acc, va);
+          for (int c0 = 0; c0 < rd.n_out; c0 += 64) {
             load32f(bias_p + c0 + 32, b1);
             tmem_ld_wait();
-            do_chunk(c0, v, b0);
-            tmem_ld32(t_acc + c0 + 32, v);
-            if (c0 + 64 < rd.n_out) load32f(bias_p + c0 + 64, b0);
+            tmem_ld32(t_acc + c0 + 32, vb);
+            do_chunk(c0, va, b0);
+            const bool more = c0 + 64 < rd.n_out;
+            if (more) load32f(bias_p + c0 + 64, b0);
             tmem_ld_wait();
-            do_chunk(c0 + 32, v, b1);
+            if (more) tmem_ld32(t_acc + c0 + 64, va);
+            do_chunk(c0 + 32, vb, b1);
           }
           if (rd.epi == MCF_EPI_RELU_SIGMA) {
             st.sigma = sig + __ldg(p.consts + rd.aux_off + rd.n_out);

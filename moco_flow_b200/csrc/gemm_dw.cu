@@ -16,9 +16,12 @@
 namespace mcf {
 
 constexpr int kDwThreads = 256;
-constexpr int kDwStages = 2;
+constexpr int kDwStages = 4;
 constexpr uint32_t kBlkD = MCF_BLOCK_BYTES;
-constexpr uint32_t kStageBytes = 2 * kBlkD + 4 * kBlkD;  // P i-block (128 cols) + Q (<=256 cols)
+constexpr uint32_t kHalf = kBlkD / 2;                    // 64 rows of one 64-column block
+// one stage = 64 rows: P i-block (2 blocks) + Q (<= 4 blocks), 8 KB each -> 48 KB; 4 stages keep ~150 KB of
+// HBM reads in flight per SM, enough to cover the DRAM latency at full bandwidth
+constexpr uint32_t kStageBytes = 2 * kHalf + 4 * kHalf;
 
 struct DwCtl {
   uint64_t full[kDwStages];
@@ -28,7 +31,7 @@ struct DwCtl {
   uint32_t pad;
 };
 constexpr uint32_t kDwOffOnes = kDwStages * kStageBytes;
-constexpr uint32_t kDwOffCtl = kDwOffOnes + kBlkD;
+constexpr uint32_t kDwOffCtl = kDwOffOnes + kHalf;
 constexpr uint32_t kDwSmem = kDwOffCtl + sizeof(DwCtl);
 
 __global__ void __launch_bounds__(kDwThreads, 1) k_dw(const __grid_constant__ mcf_dw_params_t p, int nib) {
@@ -45,11 +48,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw(const __grid_constant__ mc
   const uint32_t n_mma = q_blocks * 64u;  // whole 64-column atoms only (canonical MN-major SW128 shapes)
   const bool want_colsum = p.colsum_p != nullptr;
 
-  // ones tile: column 0 of every row = 1.0 (bf16), rest 0
-  for (int i = threadIdx.x; i < (int)(kBlkD / 16); i += kDwThreads)
+  // ones tile (64 rows): column 0 of every row = 1.0 (bf16), rest 0
+  for (int i = threadIdx.x; i < (int)(kHalf / 16); i += kDwThreads)
     reinterpret_cast<uint4*>(smem + kDwOffOnes)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  if (threadIdx.x < 128)
+  if (threadIdx.x < 64)
     *reinterpret_cast<uint16_t*>(smem + kDwOffOnes + sw128_off(threadIdx.x, 0)) = 0x3F80u;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kDwStages; ++s) {
@@ -78,12 +81,18 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw(const __grid_constant__ mc
       const uint8_t* pb = reinterpret_cast<const uint8_t*>(p.p_base);
       const uint8_t* qb = reinterpret_cast<const uint8_t*>(p.q_base);
       for (long long t = split; t < p.n_tiles; t += nsplit) {
-        mbar_wait(&ctl.empty[stage], phase ^ 1u, 0x500u | stage);
-        mbar_arrive_expect_tx(&ctl.full[stage], 2 * kBlkD + q_blocks * kBlkD);
-        uint8_t* dst = smem + stage * kStageBytes;
-        bulk_g2s(dst, pb + t * p.p_tile_bytes + p.p_off + (uint32_t)ib * 2u * kBlkD, 2 * kBlkD, &ctl.full[stage]);
-        bulk_g2s(dst + 2 * kBlkD, qb + t * p.q_tile_bytes + p.q_off, q_blocks * kBlkD, &ctl.full[stage]);
-        if (++stage == kDwStages) { stage = 0; phase ^= 1u; }
+        const uint8_t* psrc = pb + t * p.p_tile_bytes + p.p_off + (uint32_t)ib * 2u * kBlkD;
+        const uint8_t* qsrc = qb + t * p.q_tile_bytes + p.q_off;
+        for (uint32_t half = 0; half < 2; ++half) {
+          mbar_wait(&ctl.empty[stage], phase ^ 1u, 0x500u | stage);
+          mbar_arrive_expect_tx(&ctl.full[stage], (2 + q_blocks) * kHalf);
+          uint8_t* dst = smem + stage * kStageBytes;
+          for (uint32_t b = 0; b < 2; ++b)
+            bulk_g2s(dst + b * kHalf, psrc + b * kBlkD + half * kHalf, kHalf, &ctl.full[stage]);
+          for (uint32_t b = 0; b < q_blocks; ++b)
+            bulk_g2s(dst + (2 + b) * kHalf, qsrc + b * kBlkD + half * kHalf, kHalf, &ctl.full[stage]);
+          if (++stage == kDwStages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -94,22 +103,24 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw(const __grid_constant__ mc
       const uint32_t ones_addr = smem_u32(smem + kDwOffOnes);
       bool first = true;
       for (long long t = split; t < p.n_tiles; t += nsplit) {
-        mbar_wait(&ctl.full[stage], phase, 0x600u | stage);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * kStageBytes);
-        const uint32_t b_base = a_base + 2 * kBlkD;
-        for (uint32_t k = 0; k < 8; ++k) {  // 8 x 16 rows
-          const uint64_t ad = make_sdesc(a_base + k * 2048u, kBlkD, 1024u);
-          const uint64_t bd = make_sdesc(b_base + k * 2048u, kBlkD, 1024u);
-          umma_bf16(tmem_base, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
-          if (want_colsum) {
-            const uint64_t od = make_sdesc(ones_addr + k * 2048u, kBlkD, 1024u);
-            umma_bf16(tmem_base + 256, ad, od, idesc1, (first && k == 0) ? 0u : 1u);
+        for (uint32_t half = 0; half < 2; ++half) {
+          mbar_wait(&ctl.full[stage], phase, 0x600u | stage);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * kStageBytes);
+          const uint32_t b_base = a_base + 2 * kHalf;
+          for (uint32_t k = 0; k < 4; ++k) {  // 4 x 16 rows
+            const uint64_t ad = make_sdesc(a_base + k * 2048u, kHalf, 1024u);
+            const uint64_t bd = make_sdesc(b_base + k * 2048u, kHalf, 1024u);
+            umma_bf16(tmem_base, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+            if (want_colsum) {
+              const uint64_t od = make_sdesc(ones_addr + k * 2048u, kHalf, 1024u);
+              umma_bf16(tmem_base + 256, ad, od, idesc1, (first && k == 0) ? 0u : 1u);
+            }
           }
+          first = false;
+          umma_commit(&ctl.empty[stage]);
+          if (++stage == kDwStages) { stage = 0; phase ^= 1u; }
         }
-        first = false;
-        umma_commit(&ctl.empty[stage]);
-        if (++stage == kDwStages) { stage = 0; phase ^= 1u; }
       }
       umma_commit(&ctl.done);
     }
