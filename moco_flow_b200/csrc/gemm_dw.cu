@@ -31,7 +31,7 @@ struct DwCtl {
   uint32_t pad;
 };
 constexpr uint32_t kDwOffOnes = kDwStages * kStageBytes;
-constexpr uint32_t kDwOffCtl = kDwOffOnes + kHalf;
+constexpr uint32_t kDwOffCtl = kDwOffOnes + kBlkD;
 constexpr uint32_t kDwSmem = kDwOffCtl + sizeof(DwCtl);
 
 __global__ void __launch_bounds__(kDwThreads, 1) k_dw(const __grid_constant__ mcf_dw_params_t p, int nib) {
@@ -48,11 +48,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw(const __grid_constant__ mc
   const uint32_t n_mma = q_blocks * 64u;  // whole 64-column atoms only (canonical MN-major SW128 shapes)
   const bool want_colsum = p.colsum_p != nullptr;
 
-  // ones tile (64 rows): column 0 of every row = 1.0 (bf16), rest 0
-  for (int i = threadIdx.x; i < (int)(kHalf / 16); i += kDwThreads)
+  // ones tile: column 0 of every row = 1.0 (bf16), rest 0
+  for (int i = threadIdx.x; i < (int)(kBlkD / 16); i += kDwThreads)
     reinterpret_cast<uint4*>(smem + kDwOffOnes)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  if (threadIdx.x < 64)
+  if (threadIdx.x < 128)
     *reinterpret_cast<uint16_t*>(smem + kDwOffOnes + sw128_off(threadIdx.x, 0)) = 0x3F80u;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kDwStages; ++s) {
@@ -108,13 +108,19 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw(const __grid_constant__ mc
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * kStageBytes);
           const uint32_t b_base = a_base + 2 * kHalf;
+          const uint32_t acc0 = first ? 0u : 1u;
+#pragma unroll 1
           for (uint32_t k = 0; k < 4; ++k) {  // 4 x 16 rows
             const uint64_t ad = make_sdesc(a_base + k * 2048u, kHalf, 1024u);
             const uint64_t bd = make_sdesc(b_base + k * 2048u, kHalf, 1024u);
-            umma_bf16(tmem_base, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
-            if (want_colsum) {
-              const uint64_t od = make_sdesc(ones_addr + k * 2048u, kHalf, 1024u);
-              umma_bf16(tmem_base + 256, ad, od, idesc1, (first && k == 0) ? 0u : 1u);
+            umma_bf16(tmem_base, ad, bd, idesc, k == 0 ? acc0 : 1u);
+          }
+          if (want_colsum) {
+#pragma unroll 1
+            for (uint32_t k = 0; k < 4; ++k) {
+              const uint64_t ad = make_sdesc(a_base + k * 2048u, kHalf, 1024u);
+              const uint64_t od = make_sdesc(ones_addr + k * 2048u, kBlkD, 1024u);
+              umma_bf16(tmem_base + 256, ad, od, idesc1, k == 0 ? acc0 : 1u);
             }
           }
           first = false;
