@@ -23,8 +23,7 @@
 
 namespace mcf {
 
-constexpr int kEpiThreads = 256;   // per slot: 8 warps, two threads per tile row
-constexpr int kThreads = 128 + 2 * kEpiThreads;
+constexpr int kThreads = 384;
 constexpr int kStages = 4;
 constexpr uint32_t kBlk = MCF_BLOCK_BYTES;
 constexpr int kMaxChunks = 128;
@@ -119,7 +118,11 @@ __device__ __forceinline__ uint32_t bias_act_store32(uint8_t* hbuf, uint32_t row
   return word;
 }
 
-
+struct RowState {   // per-thread state that lives across the rounds of one tile
+  float sigma;      // fwd: sigma head value; bwd: d_sigma
+  float dx[3];      // bwd: accumulated d_xyz
+  float aux[4];
+};
 
 // quaternion head of NoF (models/nof.py:75-80 with kornia 0.6.5 semantics)
 __device__ __forceinline__ void nof_quat_apply(const float* h9, const float* x, float* out) {
@@ -191,90 +194,6 @@ __device__ __forceinline__ void nof_quat_backward(const float* h9, const float* 
   }
 }
 
-// TMEM -> / <- registers helpers for the partial-sum mailbox
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(a), "r"(b), "r"(c),
-               "r"(d)
-               : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
-               : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
-               : "r"(taddr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-}
-
-// The two threads that share a tile row (column halves hc = 0 / 1, same TMEM lane) exchange up to three partial
-// sums through accumulator columns the hc = 1 thread has already consumed.  Returns the other half's values to
-// the hc = 0 thread (zeros to hc = 1).  All kEpiThreads threads of the slot must call it.
-__device__ __forceinline__ void exchange_partial3(uint32_t taddr, float a0, float a1, float a2, int hc, uint32_t bar_id,
-                                                  float& o0, float& o1, float& o2) {
-  o0 = o1 = o2 = 0.f;
-  if (hc == 1) {
-    tmem_st4(taddr, __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), 0u);
-    tc_fence_before();
-  }
-  named_bar_sync(bar_id, kEpiThreads);
-  if (hc == 0) {
-    tc_fence_after();
-    uint32_t r0, r1, r2, r3;
-    tmem_ld4(taddr, r0, r1, r2, r3);
-    o0 = __uint_as_float(r0); o1 = __uint_as_float(r1); o2 = __uint_as_float(r2);
-  }
-}
-__device__ __forceinline__ float exchange_partial(uint32_t taddr, float a, int hc, uint32_t bar_id) {
-  float o0, o1, o2;
-  exchange_partial3(taddr, a, 0.f, 0.f, hc, bar_id, o0, o1, o2);
-  return o0;
-}
-
-// Positional encoding of one point, channels [32*HC, 32*HC + 32) -> four 16-byte chunks of the operand block.
-// Channel order of models/embedding.py:42-46: [x | w0 sin(f0 x) | w0 cos(f0 x) | w1 sin(f1 x) | ...].
-// Full-range sincosf at every 4th octave; in between sin/cos(2a) from sin/cos(a) (<= 3 doublings, error <= ~8
-// ulp, far below the bf16 rounding of the operand); non-octave frequency tables stay exact.
-template <int HC>
-__device__ __forceinline__ void pe_half(const mcf_chain_params_t& p, const float (&x)[3], uint32_t row,
-                                        uint8_t* x0buf) {
-  float ch[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) ch[c] = 0.f;
-  if (HC == 0) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) ch[c] = x[c];
-  }
-  float sn[3] = {0.f, 0.f, 0.f}, cs[3] = {1.f, 1.f, 1.f};
-#pragma unroll
-  for (int k = 0; k < 10; ++k) {
-    if (k < p.pe_n_freqs) {
-      const float f = p.pe_freq[k], w = p.pe_weight[k];
-      const bool exact = (k & 3) == 0 || f != 2.0f * p.pe_freq[k > 0 ? k - 1 : 0];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (exact) {
-          sincosf(f * x[c], &sn[c], &cs[c]);
-        } else {
-          const float s2 = 2.0f * sn[c] * cs[c];
-          const float c2 = fmaf(-2.0f * sn[c], sn[c], 1.0f);
-          sn[c] = s2;
-          cs[c] = c2;
-        }
-        const int is = 3 + 6 * k + c - 32 * HC, ic = is + 3;
-        if (is >= 0 && is < 32) ch[is] = w * sn[c];
-        if (ic >= 0 && ic < 32) ch[ic] = w * cs[c];
-      }
-    }
-  }
-#pragma unroll
-  for (int c8 = 0; c8 < 4; ++c8) {
-    uint4 v;
-    v.x = pack_bf16x2(ch[c8 * 8 + 0], ch[c8 * 8 + 1]); v.y = pack_bf16x2(ch[c8 * 8 + 2], ch[c8 * 8 + 3]);
-    v.z = pack_bf16x2(ch[c8 * 8 + 4], ch[c8 * 8 + 5]); v.w = pack_bf16x2(ch[c8 * 8 + 6], ch[c8 * 8 + 7]);
-    *reinterpret_cast<uint4*>(x0buf + sw128_off(row, HC * 4 + c8)) = v;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // the chain kernel
 // ---------------------------------------------------------------------------------------------
@@ -314,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       mbar_init(&tab.w_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&tab.act_ready[s], kEpiThreads);
+      mbar_init(&tab.act_ready[s], 128);
       mbar_init(&tab.acc_full[s], 1);
     }
     fence_mbar_init();
@@ -333,9 +252,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
   const long long n_pairs = (n_tiles + 1) / 2;
 
   // register re-distribution between the warpgroups: the producer/MMA/allocator warpgroup needs few registers,
-  // the two epilogue warpgroups hold 64 accumulator + 64 bias values in flight (128*56 + 512*104 <= 64K)
+  // the two epilogue warpgroups hold 64 accumulator + 64 bias values in flight (128*72 + 256*208 <= 64K)
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
   if (warp == 0) {
     // =========================== weight producer ===========================
     if (lane == 0) {
@@ -416,15 +335,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");
     // =========================== epilogue groups ===========================
-    // 8 warps per slot: two threads per tile row, each owning one half of the accumulator columns
-    const int ew = warp - 4;
-    const int s = ew >> 3;                  // slot
-    const int qtr = ew & 3;                 // TMEM lane quarter this warp may access (== warp & 3)
-    const int hc = (ew >> 2) & 1;           // column half owned by this thread
+    const int s = (warp - 4) >> 2;          // slot
+    const int qtr = warp & 3;               // TMEM lane quarter this warp may access
     const uint32_t row = qtr * 32 + lane;   // tile row owned by this thread
-    const int gtid = threadIdx.x - 128 - s * kEpiThreads;
+    const int gtid = threadIdx.x - 128 - s * 128;
     uint8_t* hbuf = smem + L::off_h + s * L::kHBytes;
     uint8_t* x0buf = smem + L::off_x0 + s * kBlk;
     const uint32_t t_row = tmem_base + ((uint32_t)(qtr * 32) << 16) + s * kSlotCols;
@@ -440,14 +356,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       const long long mc = valid ? m : (p.n_rows - 1);
       const long long ray = mc / p.rows_per_ray;
       uint8_t* save_tile = saving ? reinterpret_cast<uint8_t*>(p.save) + tile * p.save_tile_bytes : nullptr;
-      float st_sigma = 0.f;                  // fwd: sigma head value; bwd: d_sigma
-      float st_dx[3] = {0.f, 0.f, 0.f};      // bwd: accumulated d_xyz (hc == 0 threads)
+      RowState st;
+      st.sigma = 0.f; st.dx[0] = st.dx[1] = st.dx[2] = 0.f;
+      st.aux[0] = st.aux[1] = st.aux[2] = st.aux[3] = 0.f;
 
       MCF_T0(te);
       // make sure an earlier bulk store no longer reads the buffers we are about to overwrite
       if (store_pending) {
         if (gtid == 0) bulk_wait_read_all();
-        named_bar_sync(1 + s, kEpiThreads);
+        named_bar_sync(1 + s, 128);
         store_pending = false;
       }
 
@@ -455,10 +372,45 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       if (p.prologue == MCF_PRO_PE_XYZ) {
         float x[3] = {0.f, 0.f, 0.f};
         if (valid) { x[0] = p.xyz[m * 3 + 0]; x[1] = p.xyz[m * 3 + 1]; x[2] = p.xyz[m * 3 + 2]; }
-        if (hc == 0) pe_half<0>(p, x, row, x0buf); else pe_half<1>(p, x, row, x0buf);
+        // channel order of models/embedding.py:42-46: [x | w0 sin(f0 x) | w0 cos(f0 x) | w1 sin(f1 x) | ...]
+        float ch[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) ch[c] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ch[c] = x[c];
+        float sn[3] = {0.f, 0.f, 0.f}, cs[3] = {1.f, 1.f, 1.f};
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          if (k < p.pe_n_freqs) {
+            const float f = p.pe_freq[k], w = p.pe_weight[k];
+            // full-range sincosf at every 4th octave; in between sin/cos(2a) from sin/cos(a) (<= 3 doublings,
+            // error <= ~8 ulp, far below the bf16 rounding of the operand); non-octave tables stay exact
+            const bool exact = (k & 3) == 0 || f != 2.0f * p.pe_freq[k > 0 ? k - 1 : 0];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              if (exact) {
+                sincosf(f * x[c], &sn[c], &cs[c]);
+              } else {
+                const float s2 = 2.0f * sn[c] * cs[c];
+                const float c2 = fmaf(-2.0f * sn[c], sn[c], 1.0f);
+                sn[c] = s2;
+                cs[c] = c2;
+              }
+              ch[3 + 6 * k + c] = w * sn[c];
+              ch[3 + 6 * k + 3 + c] = w * cs[c];
+            }
+          }
+        }
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint4 v;
+          v.x = pack_bf16x2(ch[c8 * 8 + 0], ch[c8 * 8 + 1]); v.y = pack_bf16x2(ch[c8 * 8 + 2], ch[c8 * 8 + 3]);
+          v.z = pack_bf16x2(ch[c8 * 8 + 4], ch[c8 * 8 + 5]); v.w = pack_bf16x2(ch[c8 * 8 + 6], ch[c8 * 8 + 7]);
+          *reinterpret_cast<uint4*>(x0buf + sw128_off(row, c8)) = v;
+        }
       } else if (p.prologue == MCF_PRO_DENSE) {
         const float* src = p.dense + mc * p.dense_stride;
-        for (int c8 = hc * 4; c8 < hc * 4 + 4; ++c8) {
+        for (int c8 = 0; c8 < 8; ++c8) {
           float f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -475,36 +427,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         float4 g = valid ? *reinterpret_cast<const float4*>(p.g_out + m * 4) : make_float4(0, 0, 0, 0);
         float4 o = valid ? *reinterpret_cast<const float4*>(p.fwd_out + m * 4) : make_float4(0, 0, 0, 0);
         float d0 = g.x * o.x * (1.f - o.x), d1 = g.y * o.y * (1.f - o.y), d2 = g.z * o.z * (1.f - o.z);
-        st_sigma = g.w;
-        if (hc == 0) {
-          if (valid && p.d_head) *reinterpret_cast<float4*>(p.d_head + m * 4) = make_float4(d0, d1, d2, g.w);
-          if (saving && p.dhead_save_off != kNone) {
-            uint8_t* blk = save_tile + p.dhead_save_off;
-            uint4 v = make_uint4(pack_bf16x2(d0, d1), pack_bf16x2(d2, g.w), 0u, 0u);
-            *reinterpret_cast<uint4*>(blk + sw128_off(row, 0)) = v;
+        st.sigma = g.w;
+        if (valid && p.d_head) *reinterpret_cast<float4*>(p.d_head + m * 4) = make_float4(d0, d1, d2, g.w);
+        if (saving && p.dhead_save_off != kNone) {
+          uint8_t* blk = save_tile + p.dhead_save_off;
+          uint4 v = make_uint4(pack_bf16x2(d0, d1), pack_bf16x2(d2, g.w), 0u, 0u);
+          *reinterpret_cast<uint4*>(blk + sw128_off(row, 0)) = v;
 #pragma unroll
-            for (int c8 = 1; c8 < 8; ++c8) *reinterpret_cast<uint4*>(blk + sw128_off(row, c8)) = make_uint4(0, 0, 0, 0);
-          }
+          for (int c8 = 1; c8 < 8; ++c8) *reinterpret_cast<uint4*>(blk + sw128_off(row, c8)) = make_uint4(0, 0, 0, 0);
         }
         const mcf_round_t& r0 = tab.rounds[0];
         const int nhe = W / 2;
         const float* wrgb = p.consts + r0.aux_off;  // [3][W/2]
         const uint32_t* mk = p.fwd_masks + tile * p.fwd_mask_tile_words + r0.mask_off;
-        for (int c0 = hc * (nhe / 2); c0 < (hc + 1) * (nhe / 2); c0 += 32) {
-          float w0[32], f[32];
-          const uint32_t word = mk[(c0 >> 5) * 128 + row];
+        for (int c0 = 0; c0 < nhe; c0 += 32) {
+          float w0[32], w1[32], w2[32], f[32];
           load32f(wrgb + c0, w0);
+          load32f(wrgb + nhe + c0, w1);
+          load32f(wrgb + 2 * nhe + c0, w2);
+          const uint32_t word = mk[(c0 >> 5) * 128 + row];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = d0 * w0[j];
-          load32f(wrgb + nhe + c0, w0);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaf(d1, w0[j], f[j]);
-          load32f(wrgb + 2 * nhe + c0, w0);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = ((word >> j) & 1u) ? fmaf(d2, w0[j], f[j]) : 0.f;
+          for (int j = 0; j < 32; ++j) {
+            float v = d0 * w0[j] + d1 * w1[j] + d2 * w2[j];
+            f[j] = ((word >> j) & 1u) ? v : 0.f;
+          }
           store_h32(hbuf, row, c0, f);
         }
-      } else if (hc == 0) {  // MCF_PRO_B_NOF (16 columns: one thread per row)
+      } else {  // MCF_PRO_B_NOF
         float g[3] = {0.f, 0.f, 0.f}, hs[12];
 #pragma unroll
         for (int j = 0; j < 12; ++j) hs[j] = 0.f;
@@ -519,10 +468,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
 #pragma unroll
         for (int j = 0; j < 16; ++j) d16[j] = 0.f;
         if (p.use_quat) {
-          nof_quat_backward(hs, hs + 9, g, d16, st_dx);
+          nof_quat_backward(hs, hs + 9, g, d16, st.dx);
         } else {  // out = head3 + x   (models/nof.py:82)
           d16[0] = g[0]; d16[1] = g[1]; d16[2] = g[2];
-          st_dx[0] = g[0]; st_dx[1] = g[1]; st_dx[2] = g[2];
+          st.dx[0] = g[0]; st.dx[1] = g[1]; st.dx[2] = g[2];
         }
         if (valid && p.d_head) {
           float4* dh = reinterpret_cast<float4*>(p.d_head + m * 12);
@@ -544,7 +493,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         // per-ray feature columns as an image block, written straight to the save record
         const float* rf = p.rayfeat + ray * p.rayfeat_stride;
         uint8_t* blk = save_tile + p.extra_save_off;
-        for (int c8 = hc * 4; c8 < hc * 4 + 4; ++c8) {
+        for (int c8 = 0; c8 < 8; ++c8) {
           float f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -560,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       fence_proxy_async_smem();
       if (saving && p.x0_save_off != kNone) {
         // the prologue's operand is itself needed by the weight-gradient GEMM: store its image
-        named_bar_sync(1 + s, kEpiThreads);
+        named_bar_sync(1 + s, 128);
         if (gtid == 0) {
           const bool fwd = p.prologue == MCF_PRO_PE_XYZ || p.prologue == MCF_PRO_DENSE;
           const uint32_t nbytes = fwd ? kBlk : (p.prologue == MCF_PRO_B_NERF ? (uint32_t)(W / 2 / 64) * kBlk : kBlk);
@@ -578,20 +527,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         const float* bias_p = (rd.raybias >= 0) ? (p.raybias[rd.raybias] + ray * rd.n_out) : (p.consts + rd.const_off);
         const bool is_bias_epi = rd.epi == MCF_EPI_RELU || rd.epi == MCF_EPI_RELU_SIGMA || rd.epi == MCF_EPI_LINEAR;
         const bool is_mask_epi = rd.epi == MCF_EPI_B_MASK || rd.epi == MCF_EPI_B_MASK_SIGMA;
-        const bool split = rd.n_out >= 128;                      // two threads per row share the columns
-        const int c_lo = split ? hc * (rd.n_out >> 1) : 0;
-        const int c_hi = split ? c_lo + (rd.n_out >> 1) : (hc == 0 ? (int)rd.n_out : 0);
         // operands that do not depend on the accumulator are fetched before waiting for the tensor core
-        float b[32];
-        uint32_t mwords[4];
-        if (is_bias_epi || rd.epi == MCF_EPI_NERF_RGB) load32f(bias_p + c_lo, b);
+        float b0[32];
+        uint32_t mwords[8];
+        if (is_bias_epi) load32f(bias_p, b0);
         if (is_mask_epi && rd.mask_off != kNone) {
-          const uint32_t* mkp = p.fwd_masks + tile * p.fwd_mask_tile_words + rd.mask_off + (c_lo >> 5) * 128 + row;
+          const uint32_t* mkp = p.fwd_masks + tile * p.fwd_mask_tile_words + rd.mask_off + row;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) mwords[j] = (c_lo + j * 32 < c_hi) ? __ldg(mkp + j * 128) : 0u;
+          for (int j = 0; j < 8; ++j) mwords[j] = (j * 32 < rd.n_out) ? __ldg(mkp + j * 128) : 0u;
         } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) mwords[j] = 0xFFFFFFFFu;
+          for (int j = 0; j < 8; ++j) mwords[j] = 0xFFFFFFFFu;
         }
         MCF_TACC(2, te);
         mbar_wait(&tab.acc_full[s], af_phase, 0x400u | s);
@@ -602,20 +548,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
                               !(rd.epi == MCF_EPI_NERF_RGB && !saving);
         if (writes_h && store_pending) {
           if (gtid == 0) bulk_wait_read_all();
-          named_bar_sync(1 + s, kEpiThreads);
+          named_bar_sync(1 + s, 128);
           store_pending = false;
         }
         const uint32_t t_acc = t_row + rd.acc_col;
 
-        if (is_bias_epi) {
+        if (rd.epi == MCF_EPI_RELU || rd.epi == MCF_EPI_RELU_SIGMA || rd.epi == MCF_EPI_LINEAR) {
           const bool want_mask = p.masks != nullptr && rd.mask_off != kNone;
           uint32_t* mk = want_mask ? (p.masks + tile * p.mask_tile_words + rd.mask_off + row) : nullptr;
           float sig = 0.f;
-          for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(t_acc + c0, v);
-            if (c0 != c_lo) load32f(bias_p + c0, b);
-            tmem_ld_wait();
+          float b1[32];
+          auto do_chunk = [&](int c0, uint32_t (&v)[32], const float (&b)[32]) {
             if (rd.epi == MCF_EPI_LINEAR) {
               bias_act_store32<false, false>(hbuf, row, c0, v, b);
             } else if (rd.epi == MCF_EPI_RELU_SIGMA) {
@@ -630,103 +573,100 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             } else {
               bias_act_store32<true, false>(hbuf, row, c0, v, b);
             }
+          };
+          // TMEM loads run one 32-column chunk ahead of the math (n_out is a multiple of 64 for these rounds)
+          uint32_t va[32], vb[32];
+          tmem_ld32(t_acc, va);
+          for (int c0 = 0; c0 < rd.n_out; c0 += 64) {
+            load32f(bias_p + c0 + 32, b1);
+            tmem_ld_wait();
+            tmem_ld32(t_acc + c0 + 32, vb);
+            do_chunk(c0, va, b0);
+            const bool more = c0 + 64 < rd.n_out;
+            if (more) load32f(bias_p + c0 + 64, b0);
+            tmem_ld_wait();
+            if (more) tmem_ld32(t_acc + c0 + 64, va);
+            do_chunk(c0 + 32, vb, b1);
           }
           if (rd.epi == MCF_EPI_RELU_SIGMA) {
-            // the two column halves of a row exchange their partial dot products through a consumed accumulator column
-            const float other = exchange_partial(t_acc + (rd.n_out >> 1), sig, hc, 3 + s);
-            st_sigma = sig + other + __ldg(p.consts + rd.aux_off + rd.n_out);
-            if (hc == 0 && p.sigma_col == 0 && valid) p.out[m * p.out_stride] = st_sigma;  // sigma-only program
+            st.sigma = sig + __ldg(p.consts + rd.aux_off + rd.n_out);
+            if (p.sigma_col == 0 && valid) p.out[m * p.out_stride] = st.sigma;  // sigma-only program
           }
         } else if (rd.epi == MCF_EPI_NERF_RGB) {
           const int nhe = rd.n_out;
           const float* wrgb = p.consts + rd.aux_off;  // [3][nhe] then b_rgb[3]
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-          for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+          float a0 = __ldg(wrgb + 3 * nhe + 0), a1 = __ldg(wrgb + 3 * nhe + 1), a2 = __ldg(wrgb + 3 * nhe + 2);
+          for (int c0 = 0; c0 < nhe; c0 += 32) {
             uint32_t v[32];
-            float w0[32];
+            float f[32], b[32], w0[32];
             tmem_ld32(t_acc + c0, v);
-            if (c0 != c_lo) load32f(bias_p + c0, b);
+            load32f(bias_p + c0, b);
             tmem_ld_wait();
+            uint32_t word = 0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) add_f32x2(v[2 * j], v[2 * j + 1], b[2 * j], b[2 * j + 1]);
+            for (int j = 0; j < 32; ++j) {
+              float t = fmaxf(__uint_as_float(v[j]) + b[j], 0.f);
+              word |= (t > 0.f ? 1u : 0u) << j;
+              f[j] = t;
+            }
             load32f(wrgb + c0, w0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) a0 = fmaf(fmaxf(__uint_as_float(v[j]), 0.f), w0[j], a0);
+            for (int j = 0; j < 32; ++j) a0 = fmaf(f[j], w0[j], a0);
             load32f(wrgb + nhe + c0, w0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) a1 = fmaf(fmaxf(__uint_as_float(v[j]), 0.f), w0[j], a1);
+            for (int j = 0; j < 32; ++j) a1 = fmaf(f[j], w0[j], a1);
             load32f(wrgb + 2 * nhe + c0, w0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) a2 = fmaf(fmaxf(__uint_as_float(v[j]), 0.f), w0[j], a2);
-            if (saving) {
-              uint32_t word = 0;
-#pragma unroll
-              for (int j = 31; j >= 0; --j) word = __funnelshift_l(v[j], word, 1);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 o;
-                o.x = cvt_bf16x2_relu_bits(v[q * 8 + 0], v[q * 8 + 1]);
-                o.y = cvt_bf16x2_relu_bits(v[q * 8 + 2], v[q * 8 + 3]);
-                o.z = cvt_bf16x2_relu_bits(v[q * 8 + 4], v[q * 8 + 5]);
-                o.w = cvt_bf16x2_relu_bits(v[q * 8 + 6], v[q * 8 + 7]);
-                store_h8(hbuf, row, c0 + q * 8, o);
-              }
-              if (p.masks && rd.mask_off != kNone)
-                p.masks[tile * p.mask_tile_words + rd.mask_off + (c0 >> 5) * 128 + row] = ~word;
-            }
+            for (int j = 0; j < 32; ++j) a2 = fmaf(f[j], w0[j], a2);
+            if (saving) store_h32(hbuf, row, c0, f);
+            if (p.masks && rd.mask_off != kNone)
+              p.masks[tile * p.mask_tile_words + rd.mask_off + (c0 >> 5) * 128 + row] = word;
           }
-          float o0, o1, o2;
-          exchange_partial3(t_acc + (nhe >> 1), a0, a1, a2, hc, 3 + s, o0, o1, o2);
-          if (hc == 0 && valid) {
-            a0 += o0 + __ldg(wrgb + 3 * nhe + 0);
-            a1 += o1 + __ldg(wrgb + 3 * nhe + 1);
-            a2 += o2 + __ldg(wrgb + 3 * nhe + 2);
+          if (valid) {
             float4 o;
             o.x = 1.f / (1.f + __expf(-a0));
             o.y = 1.f / (1.f + __expf(-a1));
             o.z = 1.f / (1.f + __expf(-a2));
-            o.w = st_sigma;
+            o.w = st.sigma;
             *reinterpret_cast<float4*>(p.out + m * 4) = o;
           }
         } else if (rd.epi == MCF_EPI_NOF_HEAD) {
-          if (hc == 0) {
-            uint32_t v[16];
-            tmem_ld16(t_acc, v);
-            tmem_ld_wait();
-            float h9[9], x[3] = {0.f, 0.f, 0.f}, o[3];
+          uint32_t v[16];
+          tmem_ld16(t_acc, v);
+          tmem_ld_wait();
+          float h9[9], x[3] = {0.f, 0.f, 0.f}, o[3];
 #pragma unroll
-            for (int j = 0; j < 9; ++j) h9[j] = __uint_as_float(v[j]) + __ldg(bias_p + j);
-            if (valid) { x[0] = p.xyz[m * 3 + 0]; x[1] = p.xyz[m * 3 + 1]; x[2] = p.xyz[m * 3 + 2]; }
-            if (p.use_quat) {
-              nof_quat_apply(h9, x, o);
-            } else {
-              o[0] = h9[0] + x[0]; o[1] = h9[1] + x[1]; o[2] = h9[2] + x[2];
-            }
-            if (valid) {
-              p.out[m * 3 + 0] = o[0]; p.out[m * 3 + 1] = o[1]; p.out[m * 3 + 2] = o[2];
-              if (p.head_save) {
-                float4* hp = reinterpret_cast<float4*>(p.head_save + m * 12);
-                hp[0] = make_float4(h9[0], h9[1], h9[2], h9[3]);
-                hp[1] = make_float4(h9[4], h9[5], h9[6], h9[7]);
-                hp[2] = make_float4(h9[8], x[0], x[1], x[2]);
-              }
+          for (int j = 0; j < 9; ++j) h9[j] = __uint_as_float(v[j]) + __ldg(bias_p + j);
+          if (valid) { x[0] = p.xyz[m * 3 + 0]; x[1] = p.xyz[m * 3 + 1]; x[2] = p.xyz[m * 3 + 2]; }
+          if (p.use_quat) {
+            nof_quat_apply(h9, x, o);
+          } else {
+            o[0] = h9[0] + x[0]; o[1] = h9[1] + x[1]; o[2] = h9[2] + x[2];
+          }
+          if (valid) {
+            p.out[m * 3 + 0] = o[0]; p.out[m * 3 + 1] = o[1]; p.out[m * 3 + 2] = o[2];
+            if (p.head_save) {
+              float4* hp = reinterpret_cast<float4*>(p.head_save + m * 12);
+              hp[0] = make_float4(h9[0], h9[1], h9[2], h9[3]);
+              hp[1] = make_float4(h9[4], h9[5], h9[6], h9[7]);
+              hp[2] = make_float4(h9[8], x[0], x[1], x[2]);
             }
           }
         } else if (rd.epi == MCF_EPI_B_MASK || rd.epi == MCF_EPI_B_MASK_SIGMA || rd.epi == MCF_EPI_B_LINEAR) {
-          for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+          for (int c0 = 0; c0 < rd.n_out; c0 += 32) {
             uint32_t v[32];
             float f[32];
             tmem_ld32(t_acc + c0, v);
             uint32_t word = 0xFFFFFFFFu;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j == ((c0 - c_lo) >> 5)) word = mwords[j];
+            for (int j = 0; j < 8; ++j)
+              if (j == (c0 >> 5)) word = mwords[j];
             tmem_ld_wait();
             if (rd.epi == MCF_EPI_B_MASK_SIGMA) {
               float ws[32];
               load32f(p.consts + rd.aux_off + c0, ws);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaf(st_sigma, ws[j], __uint_as_float(v[j]));
+              for (int j = 0; j < 32; ++j) f[j] = fmaf(st.sigma, ws[j], __uint_as_float(v[j]));
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -736,69 +676,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             store_h32(hbuf, row, c0, f);
           }
         } else if (rd.epi == MCF_EPI_B_DPE) {
-          if (hc == 0) {
-            // d_xyz += J_PE(x)^T dPE, with sin/cos taken from the saved first-layer operand image
-            const uint8_t* x0img =
-                reinterpret_cast<const uint8_t*>(p.fwd_save) + tile * p.fwd_save_tile_bytes + p.fwd_x0_off;
+          // d_xyz += J_PE(x)^T dPE, with sin/cos taken from the saved first-layer operand image
+          const uint8_t* x0img = reinterpret_cast<const uint8_t*>(p.fwd_save) + tile * p.fwd_save_tile_bytes + p.fwd_x0_off;
+          float pe[64];
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {   // 32 channels at a time
-              float pe[32];
+          for (int c8 = 0; c8 < 8; ++c8) {
+            uint4 t = *reinterpret_cast<const uint4*>(x0img + sw128_off(row, c8));
+            pe[c8 * 8 + 0] = bf16_lo(t.x); pe[c8 * 8 + 1] = bf16_hi(t.x);
+            pe[c8 * 8 + 2] = bf16_lo(t.y); pe[c8 * 8 + 3] = bf16_hi(t.y);
+            pe[c8 * 8 + 4] = bf16_lo(t.z); pe[c8 * 8 + 5] = bf16_hi(t.z);
+            pe[c8 * 8 + 6] = bf16_lo(t.w); pe[c8 * 8 + 7] = bf16_hi(t.w);
+          }
+          uint32_t v0[32], v1[32];
+          tmem_ld32(t_acc, v0);
+          tmem_ld32(t_acc + 32, v1);
+          tmem_ld_wait();
+          float dpe[64];
 #pragma unroll
-              for (int c8 = 0; c8 < 4; ++c8) {
-                uint4 t = *reinterpret_cast<const uint4*>(x0img + sw128_off(row, hh * 4 + c8));
-                pe[c8 * 8 + 0] = bf16_lo(t.x); pe[c8 * 8 + 1] = bf16_hi(t.x);
-                pe[c8 * 8 + 2] = bf16_lo(t.y); pe[c8 * 8 + 3] = bf16_hi(t.y);
-                pe[c8 * 8 + 4] = bf16_lo(t.z); pe[c8 * 8 + 5] = bf16_hi(t.z);
-                pe[c8 * 8 + 6] = bf16_lo(t.w); pe[c8 * 8 + 7] = bf16_hi(t.w);
-              }
-              uint32_t v[32];
-              tmem_ld32(t_acc + hh * 32, v);
-              tmem_ld_wait();
-              // d/dx of [x | w sin(f x) | w cos(f x)]: 1, f * (w cos), -f * (w sin); channel ch pairs with ch +- 3
+          for (int j = 0; j < 32; ++j) { dpe[j] = __uint_as_float(v0[j]); dpe[32 + j] = __uint_as_float(v1[j]); }
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int chn = hh * 32 + j;
-                const float d = __uint_as_float(v[j]);
-                if (chn < 3) {
-                  st_dx[chn] += d;
-                } else if (chn < 3 + 6 * p.pe_n_freqs) {
-                  const int k = (chn - 3) / 6, q = (chn - 3) - 6 * k;   // q: 0..2 sin, 3..5 cos
-                  const float f = p.pe_freq[k];
-                  // partner value lives 3 channels away (possibly in the other 32-channel half: handled below)
-                  if (q < 3) {
-                    const int pc = chn + 3;  // w cos(f x)
-                    if (pc < (hh + 1) * 32) st_dx[q] += f * pe[pc - hh * 32] * d;
-                  } else {
-                    const int ps = chn - 3;  // w sin(f x)
-                    if (ps >= hh * 32) st_dx[q - 3] -= f * pe[ps - hh * 32] * d;
-                  }
-                }
-              }
-              // sin/cos partners that straddle the 32-channel boundary (channels 29..31 <-> 32..34)
-              if (hh == 0) {
+          for (int c = 0; c < 3; ++c) st.dx[c] += dpe[c];
 #pragma unroll
-                for (int j = 29; j < 32; ++j) {
-                  if (j >= 3 && j < 3 + 6 * p.pe_n_freqs && ((j - 3) % 6) < 3) {
-                    uint4 t = *reinterpret_cast<const uint4*>(x0img + sw128_off(row, 4));
-                    const float pv = (j == 29) ? bf16_lo(t.x) : (j == 30 ? bf16_hi(t.x) : bf16_lo(t.y));  // ch 32,33,34
-                    st_dx[(j - 3) % 6] += p.pe_freq[(j - 3) / 6] * pv * __uint_as_float(v[j]);
-                  }
-                }
-              } else {
+          for (int k = 0; k < 10; ++k) {
+            if (k < p.pe_n_freqs) {
+              const float f = p.pe_freq[k];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                  const int chn = 32 + j;
-                  if (chn < 3 + 6 * p.pe_n_freqs && ((chn - 3) % 6) >= 3) {
-                    uint4 t = *reinterpret_cast<const uint4*>(x0img + sw128_off(row, 3));
-                    const float pv = (j == 0) ? bf16_hi(t.z) : (j == 1 ? bf16_lo(t.w) : bf16_hi(t.w));  // ch 29,30,31
-                    st_dx[(chn - 3) % 6 - 3] -= p.pe_freq[(chn - 3) / 6] * pv * __uint_as_float(v[j]);
-                  }
-                }
+              for (int c = 0; c < 3; ++c) {
+                const int is = 3 + 6 * k + c, ic = is + 3;
+                st.dx[c] += f * (pe[ic] * dpe[is] - pe[is] * dpe[ic]);
               }
             }
-            if (rd.aux_off == 1u && valid && p.d_xyz) {
-              p.d_xyz[m * 3 + 0] = st_dx[0]; p.d_xyz[m * 3 + 1] = st_dx[1]; p.d_xyz[m * 3 + 2] = st_dx[2];
-            }
+          }
+          if (rd.aux_off == 1u && valid && p.d_xyz) {
+            p.d_xyz[m * 3 + 0] = st.dx[0]; p.d_xyz[m * 3 + 1] = st.dx[1]; p.d_xyz[m * 3 + 2] = st.dx[2];
           }
         }
 
@@ -807,7 +717,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         if (writes_h) {
           fence_proxy_async_smem();
           if (saving && rd.save_off != kNone) {
-            named_bar_sync(1 + s, kEpiThreads);
+            named_bar_sync(1 + s, 128);
             if (gtid == 0) {
               bulk_s2g(save_tile + rd.save_off, hbuf, ((uint32_t)rd.n_out + 63u) / 64u * kBlk);
               bulk_commit();
