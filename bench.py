@@ -181,19 +181,31 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step(rays_d, bg_d, tgt_d)
     sync_all()
+    def dbg(msg):
+        if os.environ.get("MCF_BENCH_DEBUG"):
+            sys.stderr.write(f"[bench rank {rank}] {msg}\n")
+            sys.stderr.flush()
+
+    dbg("warm-up done")
     eager_step = step
     graphed = False
     if not args.no_graph:
+        gstep = None
         try:
             from moco_flow_b200.graph import CudaGraphStep
             gstep = CudaGraphStep(eager_step, [rays_d, bg_d, tgt_d], warmup=2)
+        except Exception as exc:  # report, then measure the eager path
+            sys.stderr.write(f"[bench rank {rank}] CUDA graph capture failed ({exc!r}); timing the eager step\n")
+            gstep = None
+        ok = torch.tensor([1 if gstep is not None else 0], device=dev)
+        if world > 1:  # every rank must take the same path, or their collectives no longer match
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
             step = gstep
             graphed = True
             for _ in range(2):
                 step(rays_d, bg_d, tgt_d)
-        except Exception as exc:  # report, then measure the eager path
-            sys.stderr.write(f"[bench] CUDA graph capture failed ({exc!r}); timing the eager step\n")
-            step = eager_step
+        dbg(f"graph capture: {graphed}")
     sync_all()
     launches_per_step_eager = 0
     if graphed:  # the graph replays exactly the launches one eager step issues
@@ -216,6 +228,7 @@ def run_ours(args):
     e1.record()
     sync_all()
     launches = (launches_per_step_eager * args.steps) if graphed else (L.LAUNCHES - launches0)
+    dbg("device-resident timing done")
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
 
@@ -235,6 +248,7 @@ def run_ours(args):
     t1.record()
     sync_all()
     ms_e2e = t0.elapsed_time(t1)
+    dbg("e2e timing done")
 
     # ---- per-kernel event timing for the roofline (extra steps, not part of the numbers above) ----
     L.PROFILE = []

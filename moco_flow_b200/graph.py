@@ -26,7 +26,9 @@ class CudaGraphStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: other threads of the process (e.g. the NCCL watchdog polling events) must not invalidate
+        # the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.static_out = fn(*self.static_in)
 
     def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
