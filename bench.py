@@ -267,9 +267,18 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms, ms_e2e = times.tolist()
-    if rank != 0:
+    def finish():
+        # Hard exit for multi-rank runs: tearing down NCCL communicators that live inside captured CUDA graphs
+        # can block in ncclCommDestroy; there is nothing left to clean up at this point.
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     peaks = {}
     try:
@@ -323,8 +332,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.workload, sample_rays=args.cpu_rays, steps=1, warmup=1)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 # --------------------------------------------------------------------------------------------------
