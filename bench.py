@@ -296,15 +296,40 @@ def run_ours(args):
                         "achieved": round(rate / (1e12 if d["unit"] == "flop" else 1e9), 2),
                         "unit": "TFLOP/s" if d["unit"] == "flop" else "GB/s"}
     dom = max(agg.items(), key=lambda kv: kv[1]["ms"])[0] if agg else None
-    roofline = None
-    if dom:
-        d = agg[dom]
+    traffic_db = {}
+    try:
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+
+    def roof(tag):
+        d = agg[tag]
         tensor = d["unit"] == "flop"
         ach = d["work"] / (d["ms"] * 1e-3) / (1e12 if tensor else 1e9)
         pk = tensor_peak if tensor else hbm_peak
-        roofline = {"kernel": dom, "bound": "tensor" if tensor else "hbm", "achieved": round(ach, 2), "peak": pk,
-                    "unit": "TFLOP/s" if tensor else "GB/s", "frac": round(ach / pk, 4), "traffic": None,
-                    "peak_source": peak_src, "share_of_step": round(d["ms"] / sum(v["ms"] for v in agg.values()), 3)}
+        out = {"kernel": tag, "bound": "tensor" if tensor else "hbm", "achieved": round(ach, 2), "peak": pk,
+               "unit": "TFLOP/s" if tensor else "GB/s", "frac": round(ach / pk, 4), "traffic": None,
+               "peak_source": peak_src, "share_of_step": round(d["ms"] / sum(v["ms"] for v in agg.values()), 3),
+               "launches_per_step": d["n"] // 2,
+               "algorithmic_per_launch": round(d["work"] / max(d["n"], 1), 1)}
+        t = traffic_db.get(tag)
+        if t:  # dram__bytes_read+write of one ncu --set full capture of this kernel (profiles/), per launch
+            out["traffic"] = t.get("dram_bytes")
+            out["traffic_note"] = t.get("note")
+        return out
+
+    roofline = roof(dom) if dom else None
+    # the fused MLP chains together (the tensor-core part of the step), for the tensor-pipe target of the north star
+    chain_tags = [t for t in agg if t.startswith("nerf_") or t.startswith("nof_")]
+    mlp = None
+    if chain_tags:
+        fl = sum(agg[t]["work"] for t in chain_tags)
+        tm = sum(agg[t]["ms"] for t in chain_tags)
+        mlp = {"kernels": sorted(chain_tags), "bound": "tensor", "achieved": round(fl / (tm * 1e-3) / 1e12, 2),
+               "peak": tensor_peak, "unit": "TFLOP/s", "frac": round(fl / (tm * 1e-3) / 1e12 / tensor_peak, 4),
+               "ms_per_step": round(tm / 2, 4)}
+        best = max(chain_tags, key=lambda t: agg[t]["work"] / max(agg[t]["ms"], 1e-9))
+        mlp["best_kernel"] = roof(best)
     flops_ray = algorithmic_flops_per_ray(args.workload)
     h2d = int(rays_h.numel() + bg_h.numel() + tgt_h.numel()) * 4
     line = {
@@ -325,6 +350,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": roofline,
+        "roofline_mlp": mlp,
         "kernels": kernels,
         "model_tflops": round(total_rays * flops_ray / (ms * 1e-3) / 1e12, 2),
         "model_tensor_frac": round(total_rays * flops_ray / (ms * 1e-3) / 1e12 / (tensor_peak * world), 4),

@@ -353,5 +353,6 @@ def dw_gemm(p_base: torch.Tensor, p_tile_bytes: int, p_off: int, p_cols: int, q_
     dp.out, dp.ld_out, dp.n_i, dp.n_j = out.data_ptr(), out.stride(0), n_i, n_j
     dp.colsum_p = 0 if colsum is None else colsum.data_ptr()
     dp.n_tiles, dp.max_ctas = n_tiles, max_ctas
-    with L.timed("dw_gemm", 2.0 * n_i * n_j * n_tiles * L.TILE_ROWS, "flop"):
+    # HBM-bound by construction: every P / Q image byte is read once (2*(in+out) B per sample)
+    with L.timed("dw_gemm", 2.0 * (n_i + q_cols) * n_tiles * L.TILE_ROWS + 4.0 * n_i * n_j, "byte"):
         L.check(L.lib().mcf_dw_gemm(C.byref(dp), L.stream_ptr()), "mcf_dw_gemm")
