@@ -151,7 +151,7 @@ def run_ours(args):
     rays_h, bg_h, tgt_h = synth_batch(R, seed=1 + rank)
     rays_h, bg_h, tgt_h = rays_h.pin_memory(), bg_h.pin_memory(), tgt_h.pin_memory()
     rays_d, bg_d, tgt_d = rays_h.to(dev), bg_h.to(dev), tgt_h.to(dev)
-    flat = dp.FlatGradients(nerfs + nofs) if train else None
+    flat = dp.FlatGradients(nerfs + nofs, fused_accumulate=True) if train else None
     opt = torch.optim.Adam(flat.params, lr=5e-4, eps=1e-8, fused=True, capturable=True) if train else None
     loss_fn = mf.MSELoss()
 

@@ -221,6 +221,22 @@ typedef struct {
 } mcf_dw_params_t;
 int mcf_dw_gemm(const mcf_dw_params_t* params_host, cudaStream_t stream);
 
+/* All weight-gradient jobs of one MLP evaluation in ONE launch (grid = n_jobs x CTAs-per-job): removes the
+ * launch gaps and lets the tail of one job overlap the head of the next.  Jobs reference the forward / backward
+ * save records through a selector so that the (static) job table can stay resident on the device. */
+typedef struct {
+  uint32_t p_off, q_off;       /* byte offsets inside the tile records                        */
+  int32_t p_src, q_src;        /* 0: forward save record, 1: backward save record             */
+  int32_t p_cols, q_cols;
+  uint32_t st_off;             /* float offset of the [n_i][ld] result inside staging         */
+  int32_t ld, n_i, n_j;
+  int32_t colsum_off;          /* float offset of colsum_p inside staging, or -1              */
+  int32_t enabled;             /* 0: skip (parameter does not require grad)                   */
+} mcf_dw_job_t;
+int mcf_dw_gemm_batch(const mcf_dw_job_t* jobs_dev, int n_jobs, const void* fwd_save, long long fwd_tile_bytes,
+                      const void* bwd_save, long long bwd_tile_bytes, float* staging, long long n_tiles,
+                      int ctas_per_job, cudaStream_t stream);
+
 /* Scatter the staging results of mcf_dw_gemm into the parameter-gradient buffer:
  * dst[dst_off + r*dst_ld + c] = transposed ? src[src_off + c*src_ld + r] : src[src_off + r*src_ld + c]. */
 typedef struct {
@@ -232,6 +248,11 @@ typedef struct {
 } mcf_unpack_t;
 int mcf_unpack(const mcf_unpack_t* table_dev, int n_entries, const float* staging, float* grads,
                cudaStream_t stream);
+/* Same scatter, but entry e ADDS into dst_ptrs_host[e] (+ r*dst_ld + c): accumulates straight into existing
+ * parameter .grad tensors (one launch instead of one autograd add kernel per parameter). */
+#define MCF_MAX_UNPACK_PTRS 40
+int mcf_unpack_accumulate(const mcf_unpack_t* table_dev, int n_entries, const float* staging,
+                          float* const* dst_ptrs_host, cudaStream_t stream);
 
 /* out[c] += sum_m src[m*stride + c], c < ncols (<= 16): bias gradients of the heads */
 int mcf_colsum(const float* src, long long n_rows, int stride, int ncols, float* out, cudaStream_t stream);

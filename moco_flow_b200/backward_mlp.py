@@ -33,6 +33,7 @@ class _TrainState:
         self.bwd: Dict[bool, ops.PackedPlan] = {}
         self.grad: Dict[bool, P.GradPlan] = {}
         self.unpack_dev: Dict[bool, torch.Tensor] = {}
+        self.jobs_dev: Dict[tuple, torch.Tensor] = {}
 
 
 def _train_state(model) -> _TrainState:
@@ -43,24 +44,52 @@ def _train_state(model) -> _TrainState:
     return st
 
 
-def _run_grad_plan(gp: P.GradPlan, unpack_dev: torch.Tensor, fwd_save: torch.Tensor, fwd_tile_bytes: int,
-                   bwd_save: torch.Tensor, bwd_tile_bytes: int, n_tiles: int, d_head: torch.Tensor,
-                   wanted: set) -> torch.Tensor:
+# When True, parameter gradients are ADDED into existing ``param.grad`` tensors by the scatter kernel (one launch
+# per MLP evaluation) and autograd receives None for them, instead of one autograd accumulation kernel per
+# parameter per evaluation (~144 per training step).  Equivalent for ``loss.backward()``; not meaningful for
+# ``torch.autograd.grad``.  Switched on by ``dp.FlatGradients(..., fused_accumulate=True)``.
+ACCUMULATE_INTO_GRAD = False
+
+
+def _run_grad_plan(model, gp: P.GradPlan, st, need_dx: bool, fwd_save: torch.Tensor, fwd_tile_bytes: int,
+                   bwd_save: torch.Tensor, bwd_tile_bytes: int, n_tiles: int, d_head: torch.Tensor, wanted: set):
+    """Runs the weight-gradient GEMMs; returns the flat gradient buffer, or None when the gradients were
+    accumulated in place."""
     dev = fwd_save.device
     staging = torch.zeros(gp.staging_floats, device=dev)
-    grads = torch.zeros(gp.total_floats, device=dev)
-    src = {"fwd": (fwd_save, fwd_tile_bytes), "bwd": (bwd_save, bwd_tile_bytes)}
-    for j in gp.jobs:
-        if not any(n in wanted for n in j.params):
-            continue
-        pb, pt = src[j.p_src]
-        qb, qt = src[j.q_src]
-        out = staging[j.st_off:j.st_off + j.n_i * j.ld].view(j.n_i, j.ld)
-        cs = staging[j.colsum_off:j.colsum_off + j.n_i] if j.colsum_off >= 0 else None
-        ops.dw_gemm(pb, pt, j.p_off, j.p_cols, qb, qt, j.q_off, j.q_cols, out, j.n_i, j.n_j, n_tiles, cs)
+    key = (need_dx, frozenset(wanted))
+    jobs_dev = st.jobs_dev.get(key)
+    if jobs_dev is None:
+        jobs_dev = _dev_table(P.job_table(gp, wanted), dev)
+        st.jobs_dev[key] = jobs_dev
+    work = sum(2.0 * (j.n_i + j.q_cols) * n_tiles * L.TILE_ROWS + 4.0 * j.n_i * j.n_j for j in gp.jobs
+               if any(n in wanted for n in j.params))
+    with L.timed("dw_gemm", work, "byte"):
+        L.check(L.lib().mcf_dw_gemm_batch(L.ptr(jobs_dev), C.c_int(len(gp.jobs)), L.ptr(fwd_save),
+                                          C.c_longlong(fwd_tile_bytes), L.ptr(bwd_save), C.c_longlong(bwd_tile_bytes),
+                                          L.ptr(staging), C.c_longlong(n_tiles), C.c_int(148), L.stream_ptr()),
+                "mcf_dw_gemm_batch")
     ncols, stride, hc = gp.head_colsum
     L.check(L.lib().mcf_colsum(L.ptr(d_head), C.c_longlong(d_head.shape[0]), C.c_int(stride), C.c_int(ncols),
                                C.c_void_p(staging.data_ptr() + 4 * hc), L.stream_ptr()), "mcf_colsum")
+    unpack_dev = st.unpack_dev[need_dx]
+    if ACCUMULATE_INTO_GRAD:
+        params = dict(model.named_parameters())
+        ptrs = (C.c_void_p * len(gp.unpack_targets))()
+        for i, (name, inner) in enumerate(gp.unpack_targets):
+            if name not in wanted:
+                ptrs[i] = None
+                continue
+            prm = params[name]
+            if prm.grad is None:
+                prm.grad = torch.zeros_like(prm)
+            if not prm.grad.is_contiguous():
+                raise RuntimeError("in-place gradient accumulation needs contiguous .grad tensors")
+            ptrs[i] = prm.grad.data_ptr() + 4 * inner
+        L.check(L.lib().mcf_unpack_accumulate(L.ptr(unpack_dev), C.c_int(len(gp.unpack)), L.ptr(staging), ptrs,
+                                              L.stream_ptr()), "mcf_unpack_accumulate")
+        return None
+    grads = torch.zeros(gp.total_floats, device=dev)
     L.check(L.lib().mcf_unpack(L.ptr(unpack_dev), C.c_int(len(gp.unpack)), L.ptr(staging), L.ptr(grads),
                                L.stream_ptr()), "mcf_unpack")
     return grads
@@ -165,9 +194,10 @@ class _NeRFFn(torch.autograd.Function):
         pgrads = [None] * len(ctx.names)
         if wanted:
             gp = st.grad[need_dx]
-            flat = _run_grad_plan(gp, st.unpack_dev[need_dx], save, fwd_plan.save_tile_bytes, bsave,
+            flat = _run_grad_plan(model, gp, st, need_dx, save, fwd_plan.save_tile_bytes, bsave,
                                   bplan.save_tile_bytes, nt, d_head, wanted)
-            pgrads = _param_grads(gp, flat, ctx.names, needs)
+            if flat is not None:
+                pgrads = _param_grads(gp, flat, ctx.names, needs)
         return (None, None, None, d_xyz, None, None, None, *pgrads)
 
 
@@ -270,9 +300,10 @@ class _NoFFn(torch.autograd.Function):
         pgrads = [None] * len(ctx.names)
         if wanted:
             gp = st.grad[need_dx]
-            flat = _run_grad_plan(gp, st.unpack_dev[need_dx], save, fwd_plan.save_tile_bytes, bsave,
+            flat = _run_grad_plan(model, gp, st, need_dx, save, fwd_plan.save_tile_bytes, bsave,
                                   bplan.save_tile_bytes, nt, d_head, wanted)
-            pgrads = _param_grads(gp, flat, ctx.names, needs)
+            if flat is not None:
+                pgrads = _param_grads(gp, flat, ctx.names, needs)
         return (None, None, None, d_xyz, None, None, None, *pgrads)
 
 

@@ -796,6 +796,22 @@ __global__ void k_unpack(const mcf_unpack_t* __restrict__ table, const float* __
   }
 }
 
+struct UnpackPtrs {
+  float* d[MCF_MAX_UNPACK_PTRS];
+};
+__global__ void k_unpack_acc(const mcf_unpack_t* __restrict__ table, const float* __restrict__ staging, UnpackPtrs ptrs) {
+  const mcf_unpack_t e = table[blockIdx.x];
+  float* dst = ptrs.d[blockIdx.x];
+  if (dst == nullptr) return;
+  const int n = e.nrows * e.ncols;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+    const int r = i / e.ncols, c = i - r * e.ncols;
+    const float v = e.transposed ? staging[e.src_off + (long long)c * e.src_ld + r]
+                                 : staging[e.src_off + (long long)r * e.src_ld + c];
+    dst[(long long)r * e.dst_ld + c] += v;
+  }
+}
+
 // Column sums of a row-major [n_rows][stride] fp32 array (first ncols columns).  The array is walked as a flat,
 // fully coalesced stream; each thread keeps the running sum of the single column its flat indices map to
 // (blockDim * gridDim is a multiple of stride, so that column never changes), then shared-memory + global atomics.
@@ -822,6 +838,17 @@ int mcf_unpack(const mcf_unpack_t* table_dev, int n_entries, const float* stagin
                cudaStream_t stream) {
   if (n_entries <= 0) return 0;
   mcf::k_unpack<<<dim3(n_entries, 16), 256, 0, stream>>>(table_dev, staging, grads);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+int mcf_unpack_accumulate(const mcf_unpack_t* table_dev, int n_entries, const float* staging,
+                          float* const* dst_ptrs_host, cudaStream_t stream) {
+  if (n_entries <= 0) return 0;
+  if (n_entries > MCF_MAX_UNPACK_PTRS) return MCF_ERR_BAD_ARG;
+  mcf::UnpackPtrs ptrs;
+  for (int i = 0; i < MCF_MAX_UNPACK_PTRS; ++i) ptrs.d[i] = i < n_entries ? dst_ptrs_host[i] : nullptr;
+  mcf::k_unpack_acc<<<dim3(n_entries, 16), 256, 0, stream>>>(table_dev, staging, ptrs);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

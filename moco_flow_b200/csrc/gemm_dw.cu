@@ -34,7 +34,38 @@ constexpr uint32_t kDwOffOnes = kDwStages * kStageBytes;
 constexpr uint32_t kDwOffCtl = kDwOffOnes + kBlkD;
 constexpr uint32_t kDwSmem = kDwOffCtl + sizeof(DwCtl);
 
+struct DwBatchArgs {
+  const mcf_dw_job_t* jobs;
+  const uint8_t* base[2];
+  long long tile_bytes[2];
+  float* staging;
+  long long n_tiles;
+};
+
+__device__ __forceinline__ void dw_body(const mcf_dw_params_t& p, int nib, int cta, int n_cta);
+
 __global__ void __launch_bounds__(kDwThreads, 1) k_dw(const __grid_constant__ mcf_dw_params_t p, int nib) {
+  dw_body(p, nib, blockIdx.x, gridDim.x);
+}
+
+// one launch for a list of jobs: blockIdx.y selects the job, blockIdx.x the (i-block, split) inside it
+__global__ void __launch_bounds__(kDwThreads, 1) k_dw_batch(const __grid_constant__ DwBatchArgs a) {
+  const mcf_dw_job_t j = a.jobs[blockIdx.y];
+  if (!j.enabled) return;
+  mcf_dw_params_t p;
+  p.p_base = a.base[j.p_src]; p.p_tile_bytes = a.tile_bytes[j.p_src]; p.p_off = j.p_off; p.p_cols = j.p_cols;
+  p.q_base = a.base[j.q_src]; p.q_tile_bytes = a.tile_bytes[j.q_src]; p.q_off = j.q_off; p.q_cols = j.q_cols;
+  p.out = a.staging + j.st_off; p.ld_out = j.ld; p.n_i = j.n_i; p.n_j = j.n_j;
+  p.colsum_p = j.colsum_off >= 0 ? a.staging + j.colsum_off : nullptr;
+  p.n_tiles = a.n_tiles; p.max_ctas = 0;
+  const int nib = (j.n_i + 127) / 128;
+  int n_cta = (int)gridDim.x - ((int)gridDim.x % nib);   // CTAs of this job that take part
+  if ((long long)(n_cta / nib) > a.n_tiles) n_cta = (int)a.n_tiles * nib;
+  if ((int)blockIdx.x >= n_cta) return;
+  dw_body(p, nib, blockIdx.x, n_cta);
+}
+
+__device__ __forceinline__ void dw_body(const mcf_dw_params_t& p, int nib, int cta, int n_cta) {
   extern __shared__ __align__(1024) uint8_t smem[];
   DwCtl& ctl = *reinterpret_cast<DwCtl*>(smem + kDwOffCtl);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -42,8 +73,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw(const __grid_constant__ mc
     if (threadIdx.x == 0) atomicExch(&g_mcf_device_error, 0xA11C0001u);
     return;
   }
-  const int ib = blockIdx.x % nib;
-  const int split = blockIdx.x / nib, nsplit = gridDim.x / nib;
+  const int ib = cta % nib;
+  const int split = cta / nib, nsplit = n_cta / nib;
   const uint32_t q_blocks = (uint32_t)(p.q_cols + 63) / 64;
   const uint32_t n_mma = q_blocks * 64u;  // whole 64-column atoms only (canonical MN-major SW128 shapes)
   const bool want_colsum = p.colsum_p != nullptr;
@@ -166,6 +197,26 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw(const __grid_constant__ mc
 }
 
 }  // namespace mcf
+
+extern "C" int mcf_dw_gemm_batch(const mcf_dw_job_t* jobs_dev, int n_jobs, const void* fwd_save,
+                                 long long fwd_tile_bytes, const void* bwd_save, long long bwd_tile_bytes,
+                                 float* staging, long long n_tiles, int ctas_per_job, cudaStream_t stream) {
+  if (n_jobs <= 0 || n_tiles <= 0) return 0;
+  if (ctas_per_job < 2) return MCF_ERR_BAD_ARG;
+  mcf::DwBatchArgs a;
+  a.jobs = jobs_dev;
+  a.base[0] = reinterpret_cast<const uint8_t*>(fwd_save);
+  a.base[1] = reinterpret_cast<const uint8_t*>(bwd_save);
+  a.tile_bytes[0] = fwd_tile_bytes;
+  a.tile_bytes[1] = bwd_tile_bytes;
+  a.staging = staging;
+  a.n_tiles = n_tiles;
+  cudaError_t e = cudaFuncSetAttribute(mcf::k_dw_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mcf::kDwSmem);
+  if (e != cudaSuccess) return (int)e;
+  mcf::k_dw_batch<<<dim3((unsigned)ctas_per_job, (unsigned)n_jobs), mcf::kDwThreads, mcf::kDwSmem, stream>>>(a);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
 
 extern "C" int mcf_dw_gemm(const mcf_dw_params_t* pp, cudaStream_t stream) {
   if (!pp) return MCF_ERR_BAD_ARG;

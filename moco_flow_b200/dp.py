@@ -30,7 +30,13 @@ def shard_rays(rays: torch.Tensor, rank: int, world: int) -> torch.Tensor:
 class FlatGradients:
     """Flat gradient buffer shared by a list of modules; ``p.grad`` are views, so autograd accumulates in place."""
 
-    def __init__(self, modules: Iterable[torch.nn.Module]):
+    def __init__(self, modules: Iterable[torch.nn.Module], fused_accumulate: bool = False):
+        """``fused_accumulate``: let the fused MLP backward add its weight gradients straight into these ``.grad``
+        views (moco_flow_b200.backward_mlp.ACCUMULATE_INTO_GRAD) instead of going through autograd's per-parameter
+        accumulation kernels.  Process-wide switch; use only with ``loss.backward()``."""
+        if fused_accumulate:
+            from . import backward_mlp
+            backward_mlp.ACCUMULATE_INTO_GRAD = True
         self.params: List[torch.nn.Parameter] = []
         seen = set()
         for m in modules:

@@ -256,6 +256,7 @@ class GradJob:
 class GradPlan:
     jobs: List[GradJob]
     unpack: np.ndarray           # UNPACK_DT entries staging -> flat gradient buffer
+    unpack_targets: List[tuple]  # per unpack entry: (parameter name, float offset inside that parameter)
     staging_floats: int
     head_colsum: tuple           # (ncols, stride, staging float offset) of the fp32 head-gradient column sums
     param_names: List[str]
@@ -268,6 +269,7 @@ class _GradBuilder:
     def __init__(self, shapes: Dict[str, tuple]):
         self.jobs: List[GradJob] = []
         self.unpack: List[tuple] = []
+        self.targets: List[tuple] = []
         self.st = 0
         self.names = list(shapes)
         self.shapes = dict(shapes)
@@ -294,11 +296,14 @@ class _GradBuilder:
     def scatter(self, src_off, src_ld, name, row0, col0, nrows, ncols, transposed=False):
         shp = self.shapes[name]
         dst_ld = shp[1] if len(shp) == 2 else shp[0]
-        dst = self.offsets[name] + (row0 * dst_ld + col0 if len(shp) == 2 else col0)
+        inner = row0 * dst_ld + col0 if len(shp) == 2 else col0
+        dst = self.offsets[name] + inner
         self.unpack.append((src_off, dst, src_ld, dst_ld, nrows, ncols, int(transposed), 0))
+        self.targets.append((name, inner))
 
     def finish(self, head_colsum) -> GradPlan:
-        return GradPlan(self.jobs, np.array(self.unpack, dtype=L.UNPACK_DT), max(self.st, 4), head_colsum,
+        return GradPlan(self.jobs, np.array(self.unpack, dtype=L.UNPACK_DT), list(self.targets), max(self.st, 4),
+                        head_colsum,
                         self.names, self.offsets, self.shapes, self.total)
 
 
@@ -326,6 +331,15 @@ def _bwd_trunk(b: _Builder, fwd: Plan, D: int, W: int, cx: int, skips, skip_extr
                 img = b.image(wname, base + nh * 128, 128, 64 * kb, 64, ld, True, 128)
                 b.chunk(img, 1, kb, 4, 128, nh * 128, init=(kb == 0))
         b.round(L.EPI_B_MASK, W, 0, c0, save_off=b.save_slot(f"dy{i}", nkb), mask_off=fwd.offsets[f"mask_h{i}"])
+
+
+def job_table(gp: "GradPlan", wanted: set) -> np.ndarray:
+    """Device job table (mcf_dw_job_t) of a gradient plan; jobs feeding no wanted parameter are disabled."""
+    rows = []
+    for j in gp.jobs:
+        rows.append((j.p_off, j.q_off, 0 if j.p_src == "fwd" else 1, 0 if j.q_src == "fwd" else 1, j.p_cols, j.q_cols,
+                     j.st_off, j.ld, j.n_i, j.n_j, j.colsum_off, int(any(n in wanted for n in j.params))))
+    return np.array(rows, dtype=L.DWJOB_DT)
 
 
 def nerf_backward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: int, need_dx: bool,

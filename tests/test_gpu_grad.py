@@ -214,3 +214,42 @@ def test_render_rays_training_step(dev, golden_dir, name):
         # end to end the emulated oracle and the kernels can still pick different fine samples / mask members
         # (discontinuous steps), hence the wider band than in the module-level tests
         compare_grads(f"{name}.{tag}", got, list(zip(names, gem[sl])), 8e-2, list(zip(names, g32[sl])), min_cos=0.8)
+
+
+def test_fused_gradient_accumulation_matches_autograd(dev):
+    """dp.FlatGradients(fused_accumulate=True): gradients added by the scatter kernel == autograd accumulation."""
+    import moco_flow_b200 as mf
+    from moco_flow_b200 import backward_mlp, dp
+    gen = torch.Generator().manual_seed(5)
+    R, S = 9, 32
+    xyz = ((torch.rand(R * S, 3, generator=gen) - 0.5) * 1.2).to(dev)
+    ind = (torch.rand(R, 1, generator=gen) * 2 - 1).to(dev)
+    up = torch.randn(R * S, 3, generator=gen).to(dev)
+    m = mf.NoF(4, 128, 33, [2], "ind", 33, True)
+    m.load_state_dict(orc.make_nof_params(orc.C2F_NOF, 41, scale_head=0.5))
+    m = m.to(dev)
+    pe, pe_i = mf.Embedding(3, 5), mf.Embedding(1, 16)
+
+    def run():
+        out = m.evaluate(xyz=xyz, pe=pe, ray_feat=pe_i(ind), rows_per_ray=S)
+        out2 = m.evaluate(xyz=out, pe=pe, ray_feat=pe_i(ind), rows_per_ray=S)  # same module twice: grads accumulate
+        (out2 * up).sum().backward()
+
+    run()
+    ref = [p.grad.clone() for p in m.parameters()]
+    for p in m.parameters():
+        p.grad = None
+    try:
+        flat = dp.FlatGradients([m], fused_accumulate=True)
+        assert backward_mlp.ACCUMULATE_INTO_GRAD
+        flat.zero()
+        run()
+        torch.cuda.synchronize()
+        off = 0
+        for p, r in zip(m.parameters(), ref):
+            got = flat.buffer[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            # fp32 atomics in the GEMM epilogue make the summation order vary between runs
+            assert rel_fro(got, r) <= 1e-4
+    finally:
+        backward_mlp.ACCUMULATE_INTO_GRAD = False
