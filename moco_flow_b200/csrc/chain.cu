@@ -30,7 +30,6 @@ constexpr int kMaxChunks = 128;
 constexpr int kMaxRounds = 24;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr uint32_t kSlotCols = 256;
-constexpr uint32_t kStageRays = 8;
 
 struct Tables {
   mcf_chunk_t chunks[kMaxChunks];  // 2048 B
@@ -51,11 +50,7 @@ struct Smem {
   static constexpr uint32_t off_x0 = off_h + 2 * kHBytes;
   static constexpr uint32_t off_ring = off_x0 + 2 * kBlk;
   static constexpr uint32_t off_tab = off_ring + kStages * kBlk;
-  // W=128 (NoF) has shared memory to spare: per-ray bias rows of the rays a tile touches are staged here
-  // ([slot][2 folded layers][kStageRays][128] fp32) so the epilogue reads them at shared-memory latency
-  static constexpr uint32_t off_rb = off_tab + ((sizeof(Tables) + 15u) / 16u) * 16u;
-  static constexpr uint32_t kRbFloatsPerSlot = (W == 128) ? 2u * kStageRays * 128u : 0u;
-  static constexpr uint32_t total = off_rb + 2u * kRbFloatsPerSlot * 4u;
+  static constexpr uint32_t total = off_tab + sizeof(Tables);
 };
 static_assert(Smem<256>::total <= 232448, "shared memory budget exceeded");
 
@@ -121,18 +116,6 @@ __device__ __forceinline__ uint32_t bias_act_store32(uint8_t* hbuf, uint32_t row
     store_h8(hbuf, row, col0 + q * 8, o);
   }
   return word;
-}
-
-// same as load32f but through generic loads (the source may be shared memory)
-__device__ __forceinline__ void load32f_any(const float* p, float (&b)[32]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    float4 t = *(reinterpret_cast<const float4*>(p) + q);
-    b[q * 4 + 0] = t.x;
-    b[q * 4 + 1] = t.y;
-    b[q * 4 + 2] = t.z;
-    b[q * 4 + 3] = t.w;
-  }
 }
 
 struct RowState {   // per-thread state that lives across the rounds of one tile
@@ -364,9 +347,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     const bool saving = p.save != nullptr;
     uint32_t af_phase = 0;
     bool store_pending = false;
-    bool rb_stageable = W == 128 && (p.raybias[0] != nullptr || p.raybias[1] != nullptr) && p.raybias[2] == nullptr;
-    for (int r = 0; r < p.n_rounds; ++r)
-      if (tab.rounds[r].raybias >= 0 && tab.rounds[r].n_out != 128) rb_stageable = false;
 
     for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const long long tile = 2 * pair + s;
@@ -386,28 +366,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         if (gtid == 0) bulk_wait_read_all();
         named_bar_sync(1 + s, 128);
         store_pending = false;
-      }
-
-      // stage the per-ray bias rows this tile needs (W = 128 only; falls back to global loads otherwise)
-      bool rb_staged = false;
-      long long ray0 = 0;
-      float* rb_slot = reinterpret_cast<float*>(smem + L::off_rb) + s * L::kRbFloatsPerSlot;
-      if (rb_stageable) {
-        ray0 = (tile * MCF_TILE_ROWS) / p.rows_per_ray;
-        long long last_row = tile * MCF_TILE_ROWS + MCF_TILE_ROWS - 1;
-        if (last_row >= p.n_rows) last_row = p.n_rows - 1;
-        const int nr = (int)(last_row / p.rows_per_ray - ray0) + 1;
-        if (nr <= (int)kStageRays) {
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            if (p.raybias[k] != nullptr) {
-              const float* src = p.raybias[k] + ray0 * 128;
-              for (int i = gtid; i < nr * 128; i += 128) rb_slot[k * kStageRays * 128 + i] = __ldg(src + i);
-            }
-          }
-          rb_staged = true;
-          named_bar_sync(1 + s, 128);
-        }
       }
 
       // ------------------------- prologue: build the first operand -------------------------
@@ -566,16 +524,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       // ------------------------------- rounds -------------------------------
       for (int r = 0; r < p.n_rounds; ++r) {
         const mcf_round_t rd = tab.rounds[r];
-        const bool bias_smem = rb_staged && rd.raybias >= 0 && rd.raybias < 2;
-        const float* bias_p = bias_smem ? (rb_slot + rd.raybias * kStageRays * 128 + (ray - ray0) * 128)
-                              : (rd.raybias >= 0) ? (p.raybias[rd.raybias] + ray * rd.n_out)
-                                                  : (p.consts + rd.const_off);
+        const float* bias_p = (rd.raybias >= 0) ? (p.raybias[rd.raybias] + ray * rd.n_out) : (p.consts + rd.const_off);
         const bool is_bias_epi = rd.epi == MCF_EPI_RELU || rd.epi == MCF_EPI_RELU_SIGMA || rd.epi == MCF_EPI_LINEAR;
         const bool is_mask_epi = rd.epi == MCF_EPI_B_MASK || rd.epi == MCF_EPI_B_MASK_SIGMA;
         // operands that do not depend on the accumulator are fetched before waiting for the tensor core
         float b0[32];
         uint32_t mwords[8];
-        if (is_bias_epi) { if (bias_smem) load32f_any(bias_p, b0); else load32f(bias_p, b0); }
+        if (is_bias_epi) load32f(bias_p, b0);
         if (is_mask_epi && rd.mask_off != kNone) {
           const uint32_t* mkp = p.fwd_masks + tile * p.fwd_mask_tile_words + rd.mask_off + row;
 #pragma unroll
@@ -623,12 +578,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           uint32_t va[32], vb[32];
           tmem_ld32(t_acc, va);
           for (int c0 = 0; c0 < rd.n_out; c0 += 64) {
-            if (bias_smem) load32f_any(bias_p + c0 + 32, b1); else load32f(bias_p + c0 + 32, b1);
+            load32f(bias_p + c0 + 32, b1);
             tmem_ld_wait();
             tmem_ld32(t_acc + c0 + 32, vb);
             do_chunk(c0, va, b0);
             const bool more = c0 + 64 < rd.n_out;
-            if (more) { if (bias_smem) load32f_any(bias_p + c0 + 64, b0); else load32f(bias_p + c0 + 64, b0); }
+            if (more) load32f(bias_p + c0 + 64, b0);
             tmem_ld_wait();
             if (more) tmem_ld32(t_acc + c0 + 64, va);
             do_chunk(c0 + 32, vb, b1);
