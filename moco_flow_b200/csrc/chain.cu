@@ -24,7 +24,8 @@
 namespace mcf {
 
 constexpr int kThreads = 384;
-constexpr int kStages = 4;
+constexpr int kStages = 4;      // ring stages in the dedicated ring region
+constexpr int kMaxStages = 8;   // single-slot mode adds the idle slot's activation buffer as four more stages
 constexpr uint32_t kBlk = MCF_BLOCK_BYTES;
 constexpr int kMaxChunks = 128;
 constexpr int kMaxRounds = 24;
@@ -34,8 +35,8 @@ constexpr uint32_t kSlotCols = 256;
 struct Tables {
   mcf_chunk_t chunks[kMaxChunks];  // 2048 B
   mcf_round_t rounds[kMaxRounds];  // 768 B
-  uint64_t w_full[kStages];
-  uint64_t w_empty[kStages];
+  uint64_t w_full[kMaxStages];
+  uint64_t w_empty[kMaxStages];
   uint64_t act_ready[2];
   uint64_t acc_full[2];
   uint32_t tmem_base;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     for (int i = threadIdx.x; i < (int)(2 * kBlk / 16); i += kThreads) x0z[i] = make_uint4(0, 0, 0, 0);
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&tab.w_full[s], 1);
       mbar_init(&tab.w_empty[s], 1);
     }
@@ -249,7 +250,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
   const uint32_t tmem_base = tab.tmem_base;
 
   const long long n_tiles = (p.n_rows + MCF_TILE_ROWS - 1) / MCF_TILE_ROWS;
-  const long long n_pairs = (n_tiles + 1) / 2;
+  const int nslots = (W == 256 && p.n_slots == 1) ? 1 : 2;
+  const long long n_pairs = (n_tiles + nslots - 1) / nslots;   // groups of nslots tiles
+  const uint32_t nstages = nslots == 1 ? (uint32_t)kMaxStages : (uint32_t)kStages;
+  // byte offset of ring stage `st`: the ring region, then (single-slot mode) the unused slot-1 activation buffer
+  auto stage_off = [&](uint32_t st) -> uint32_t {
+    return st < (uint32_t)kStages ? L::off_ring + st * kBlk : L::off_h + L::kHBytes + (st - (uint32_t)kStages) * kBlk;
+  };
 
   // register re-distribution between the warpgroups: the producer/MMA/allocator warpgroup needs few registers,
   // the two epilogue warpgroups hold 64 accumulator + 64 bias values in flight (128*72 + 256*208 <= 64K)
@@ -263,16 +270,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int r = 0; r < p.n_rounds; ++r) {
           const int cb = tab.rounds[r].chunk_begin, ce = tab.rounds[r].chunk_end;
-          for (int s = 0; s < 2; ++s) {
-            if (2 * pair + s >= n_tiles) continue;
+          for (int s = 0; s < nslots; ++s) {
+            if (nslots * pair + s >= n_tiles) continue;
             for (int c = cb; c < ce; ++c) {
               MCF_T0(tw);
               mbar_wait(&tab.w_empty[stage], phase ^ 1u, 0x100u | stage);
               MCF_TACC(0, tw);
               const uint32_t bytes = tab.chunks[c].bytes;
               mbar_arrive_expect_tx(&tab.w_full[stage], bytes);
-              bulk_g2s(smem + L::off_ring + stage * kBlk, wsrc + tab.chunks[c].src_off, bytes, &tab.w_full[stage]);
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              bulk_g2s(smem + stage_off(stage), wsrc + tab.chunks[c].src_off, bytes, &tab.w_full[stage]);
+              if (++stage == nstages) { stage = 0; phase ^= 1u; }
             }
           }
         }
@@ -285,12 +292,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       uint32_t stage = 0, phase = 0;
       uint32_t ar_phase[2] = {0u, 0u};
       const uint32_t h_addr = smem_u32(smem + L::off_h), x0_addr = smem_u32(smem + L::off_x0);
-      const uint32_t ring_addr = smem_u32(smem + L::off_ring);
+      const uint32_t smem_base_addr = smem_u32(smem);
       for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int r = 0; r < p.n_rounds; ++r) {
           const int cb = tab.rounds[r].chunk_begin, ce = tab.rounds[r].chunk_end;
-          for (int s = 0; s < 2; ++s) {
-            if (2 * pair + s >= n_tiles) continue;
+          for (int s = 0; s < nslots; ++s) {
+            if (nslots * pair + s >= n_tiles) continue;
             MCF_T0(tm);
             mbar_wait(&tab.act_ready[s], ar_phase[s], 0x200u | s);
             ar_phase[s] ^= 1u;
@@ -306,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
               tc_fence_after();
               MCF_TACC(1, tm);
               const uint32_t a_base = (ch.a_buf ? (h_addr + s * L::kHBytes) : (x0_addr + s * kBlk)) + ch.a_kblock * kBlk;
-              const uint32_t b_base = ring_addr + stage * kBlk;
+              const uint32_t b_base = smem_base_addr + stage_off(stage);
               const uint32_t idesc = make_idesc(fuse ? 2u * ch.n : (uint32_t)ch.n);
               const uint32_t d_tmem = tmem_base + s * kSlotCols + ch.acc_col;
               for (uint32_t k = 0; k < ch.ksteps; ++k) {
@@ -315,10 +322,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
                 umma_bf16(d_tmem, ad, bd, idesc, (k > 0u || !(ch.flags & 1u)) ? 1u : 0u);
               }
               umma_commit(&tab.w_empty[stage]);
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              if (++stage == nstages) { stage = 0; phase ^= 1u; }
               if (fuse) {
                 umma_commit(&tab.w_empty[stage]);
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                if (++stage == nstages) { stage = 0; phase ^= 1u; }
                 ++c;
               }
               MCF_TACC(2, tm);
@@ -349,7 +356,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     bool store_pending = false;
 
     for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const long long tile = 2 * pair + s;
+      if (s >= nslots) break;
+      const long long tile = nslots * pair + s;
       if (tile >= n_tiles) break;
       const long long m = tile * MCF_TILE_ROWS + row;
       const bool valid = m < p.n_rows;
@@ -908,7 +916,8 @@ int mcf_chain_launch(const mcf_chain_params_t* pp, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
   }
   long long n_tiles = (p.n_rows + MCF_TILE_ROWS - 1) / MCF_TILE_ROWS;
-  long long n_pairs = (n_tiles + 1) / 2;
+  const int nslots = (p.width == 256 && p.n_slots == 1) ? 1 : 2;
+  long long n_pairs = (n_tiles + nslots - 1) / nslots;
   int cap = p.max_ctas > 0 ? p.max_ctas : n_sm;
   int grid = (int)(n_pairs < cap ? n_pairs : cap);
   cudaError_t e;
