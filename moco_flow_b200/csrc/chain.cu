@@ -23,22 +23,27 @@
 
 namespace mcf {
 
-constexpr int kThreads = 384;
+constexpr int kMaxSlots = 4;
+// tiles in flight per CTA: the 128-wide chain (NoF) is latency bound and small -> three slots; 256-wide -> two
+template <int W> struct Cfg {
+  static constexpr int kSlots = (W == 128) ? 3 : 2;
+  static constexpr int kThreads = 128 + 128 * kSlots;
+  static constexpr uint32_t kSlotCols = (W == 128) ? 128u : 256u;   // TMEM columns per slot
+};
 constexpr int kStages = 4;      // ring stages in the dedicated ring region
 constexpr int kMaxStages = 8;   // single-slot mode adds the idle slot's activation buffer as four more stages
 constexpr uint32_t kBlk = MCF_BLOCK_BYTES;
-constexpr int kMaxChunks = 128;
+constexpr int kMaxChunks = 120;
 constexpr int kMaxRounds = 24;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-constexpr uint32_t kSlotCols = 256;
 
 struct Tables {
   mcf_chunk_t chunks[kMaxChunks];  // 2048 B
   mcf_round_t rounds[kMaxRounds];  // 768 B
   uint64_t w_full[kMaxStages];
   uint64_t w_empty[kMaxStages];
-  uint64_t act_ready[2];
-  uint64_t acc_full[2];
+  uint64_t act_ready[kMaxSlots];
+  uint64_t acc_full[kMaxSlots];
   uint32_t tmem_base;
   uint32_t pad[3];
 };
@@ -47,13 +52,14 @@ template <int W>
 struct Smem {
   static constexpr uint32_t kHBlocks = W / 64;
   static constexpr uint32_t kHBytes = kHBlocks * kBlk;
+  static constexpr uint32_t kSlots = Cfg<W>::kSlots;
   static constexpr uint32_t off_h = 0;
-  static constexpr uint32_t off_x0 = off_h + 2 * kHBytes;
-  static constexpr uint32_t off_ring = off_x0 + 2 * kBlk;
+  static constexpr uint32_t off_x0 = off_h + kSlots * kHBytes;
+  static constexpr uint32_t off_ring = off_x0 + kSlots * kBlk;
   static constexpr uint32_t off_tab = off_ring + kStages * kBlk;
   static constexpr uint32_t total = off_tab + sizeof(Tables);
 };
-static_assert(Smem<256>::total <= 232448, "shared memory budget exceeded");
+static_assert(Smem<256>::total <= 232448 && Smem<128>::total <= 232448, "shared memory budget exceeded");
 
 // ---------------------------------------------------------------------------------------------
 // epilogue helpers (thread == row)
@@ -203,10 +209,14 @@ __device__ __forceinline__ void nof_quat_backward(const float* h9, const float* 
   do { if (timing) { long long _n = clock64(); tacc[slot] += (unsigned long long)(_n - var); var = _n; } } while (0)
 
 template <int W>
-__global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ mcf_chain_params_t p) {
+__global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_constant__ mcf_chain_params_t p) {
+  constexpr int kThreads = Cfg<W>::kThreads;
+  constexpr int kSlots = Cfg<W>::kSlots;
+  constexpr uint32_t kSlotCols = Cfg<W>::kSlotCols;
   extern __shared__ __align__(1024) uint8_t smem[];
   const bool timing = p.timing != nullptr;
   unsigned long long tacc[4] = {0ull, 0ull, 0ull, 0ull};
+  unsigned long long tfine[2] = {0ull, 0ull};
   const long long t_kernel0 = timing ? clock64() : 0;
   using L = Smem<W>;
   Tables& tab = *reinterpret_cast<Tables*>(smem + L::off_tab);
@@ -226,14 +236,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     uint32_t* dst_r = reinterpret_cast<uint32_t*>(tab.rounds);
     for (int i = threadIdx.x; i < p.n_rounds * 8; i += kThreads) dst_r[i] = src_r[i];
     uint4* x0z = reinterpret_cast<uint4*>(smem + L::off_x0);
-    for (int i = threadIdx.x; i < (int)(2 * kBlk / 16); i += kThreads) x0z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (int)(kSlots * kBlk / 16); i += kThreads) x0z[i] = make_uint4(0, 0, 0, 0);
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&tab.w_full[s], 1);
       mbar_init(&tab.w_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxSlots; ++s) {
       mbar_init(&tab.act_ready[s], 128);
       mbar_init(&tab.acc_full[s], 1);
     }
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
   const uint32_t tmem_base = tab.tmem_base;
 
   const long long n_tiles = (p.n_rows + MCF_TILE_ROWS - 1) / MCF_TILE_ROWS;
-  const int nslots = (W == 256 && p.n_slots == 1) ? 1 : 2;
+  const int nslots = (W == 256 && p.n_slots == 1) ? 1 : kSlots;
   const long long n_pairs = (n_tiles + nslots - 1) / nslots;   // groups of nslots tiles
   const uint32_t nstages = nslots == 1 ? (uint32_t)kMaxStages : (uint32_t)kStages;
   // byte offset of ring stage `st`: the ring region, then (single-slot mode) the unused slot-1 activation buffer
@@ -261,7 +271,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
   // register re-distribution between the warpgroups: the producer/MMA/allocator warpgroup needs few registers,
   // the two epilogue warpgroups hold 64 accumulator + 64 bias values in flight (128*72 + 256*208 <= 64K)
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+  if (W == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
   if (warp == 0) {
     // =========================== weight producer ===========================
     if (lane == 0) {
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      uint32_t ar_phase[2] = {0u, 0u};
+      uint32_t ar_phase[kMaxSlots] = {0u, 0u, 0u, 0u};
       const uint32_t h_addr = smem_u32(smem + L::off_h), x0_addr = smem_u32(smem + L::off_x0);
       const uint32_t smem_base_addr = smem_u32(smem);
       for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -342,7 +353,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");
+    // 256-wide: 128*72 + 256*208 <= 64K registers; 128-wide (three slots): 128*56 + 384*152 = 64K
+    if (W == 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;\n");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");
     // =========================== epilogue groups ===========================
     const int s = (warp - 4) >> 2;          // slot
     const int qtr = warp & 3;               // TMEM lane quarter this warp may access
@@ -587,14 +600,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           tmem_ld32(t_acc, va);
           for (int c0 = 0; c0 < rd.n_out; c0 += 64) {
             load32f(bias_p + c0 + 32, b1);
+            long long tq = timing ? clock64() : 0;
             tmem_ld_wait();
+            if (timing) { long long n = clock64(); tfine[0] += (unsigned long long)(n - tq); tq = n; }
             tmem_ld32(t_acc + c0 + 32, vb);
             do_chunk(c0, va, b0);
+            if (timing) { long long n = clock64(); tfine[1] += (unsigned long long)(n - tq); tq = n; }
             const bool more = c0 + 64 < rd.n_out;
             if (more) load32f(bias_p + c0 + 64, b0);
             tmem_ld_wait();
+            if (timing) { long long n = clock64(); tfine[0] += (unsigned long long)(n - tq); tq = n; }
             if (more) tmem_ld32(t_acc + c0 + 64, va);
             do_chunk(c0 + 32, vb, b1);
+            if (timing) { long long n = clock64(); tfine[1] += (unsigned long long)(n - tq); }
           }
           if (rd.epi == MCF_EPI_RELU_SIGMA) {
             st.sigma = sig + __ldg(p.consts + rd.aux_off + rd.n_out);
@@ -741,6 +759,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     if (timing && gtid == 0) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) p.timing[blockIdx.x * 16 + s * 4 + j] = tacc[j];
+      if (s == 0) { p.timing[blockIdx.x * 16 + 13] = tfine[0]; p.timing[blockIdx.x * 16 + 14] = tfine[1]; }
     }
   }
 
@@ -916,7 +935,7 @@ int mcf_chain_launch(const mcf_chain_params_t* pp, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
   }
   long long n_tiles = (p.n_rows + MCF_TILE_ROWS - 1) / MCF_TILE_ROWS;
-  const int nslots = (p.width == 256 && p.n_slots == 1) ? 1 : 2;
+  const int nslots = (p.width == 256 && p.n_slots == 1) ? 1 : (p.width == 128 ? mcf::Cfg<128>::kSlots : mcf::Cfg<256>::kSlots);
   long long n_pairs = (n_tiles + nslots - 1) / nslots;
   int cap = p.max_ctas > 0 ? p.max_ctas : n_sm;
   int grid = (int)(n_pairs < cap ? n_pairs : cap);
@@ -925,12 +944,12 @@ int mcf_chain_launch(const mcf_chain_params_t* pp, cudaStream_t stream) {
     const int smem = (int)mcf::Smem<256>::total;
     e = cudaFuncSetAttribute(mcf::k_chain<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    mcf::k_chain<256><<<grid, mcf::kThreads, smem, stream>>>(p);
+    mcf::k_chain<256><<<grid, mcf::Cfg<256>::kThreads, smem, stream>>>(p);
   } else if (p.width == 128) {
     const int smem = (int)mcf::Smem<128>::total;
     e = cudaFuncSetAttribute(mcf::k_chain<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    mcf::k_chain<128><<<grid, mcf::kThreads, smem, stream>>>(p);
+    mcf::k_chain<128><<<grid, mcf::Cfg<128>::kThreads, smem, stream>>>(p);
   } else {
     return MCF_ERR_UNSUPPORTED;
   }
