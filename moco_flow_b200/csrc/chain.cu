@@ -24,9 +24,9 @@
 namespace mcf {
 
 constexpr int kMaxSlots = 4;
-// tiles in flight per CTA: the 128-wide chain (NoF) is latency bound and small -> three slots; 256-wide -> two
+// tiles in flight per CTA (three for the 128-wide chain was measured slower: the MMA issue rate dropped)
 template <int W> struct Cfg {
-  static constexpr int kSlots = (W == 128) ? 3 : 2;
+  static constexpr int kSlots = 2;
   static constexpr int kThreads = 128 + 128 * kSlots;
   static constexpr uint32_t kSlotCols = (W == 128) ? 128u : 256u;   // TMEM columns per slot
 };
@@ -263,6 +263,9 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
   const int nslots = (W == 256 && p.n_slots == 1) ? 1 : kSlots;
   const long long n_pairs = (n_tiles + nslots - 1) / nslots;   // groups of nslots tiles
   const uint32_t nstages = nslots == 1 ? (uint32_t)kMaxStages : (uint32_t)kStages;
+  // n_slots == 3: both slots run the same layer at the same time and share every weight chunk (half the weight
+  // traffic per FLOP, no ping-pong between the tensor core and the epilogues)
+  const bool lockstep = p.n_slots == 3 && nslots == 2;
   // byte offset of ring stage `st`: the ring region, then (single-slot mode) the unused slot-1 activation buffer
   auto stage_off = [&](uint32_t st) -> uint32_t {
     return st < (uint32_t)kStages ? L::off_ring + st * kBlk : L::off_h + L::kHBytes + (st - (uint32_t)kStages) * kBlk;
@@ -271,8 +274,7 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
   // register re-distribution between the warpgroups: the producer/MMA/allocator warpgroup needs few registers,
   // the two epilogue warpgroups hold 64 accumulator + 64 bias values in flight (128*72 + 256*208 <= 64K)
   if (warp < 4) {
-  if (W == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
-  else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
   if (warp == 0) {
     // =========================== weight producer ===========================
     if (lane == 0) {
@@ -281,7 +283,9 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
       for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int r = 0; r < p.n_rounds; ++r) {
           const int cb = tab.rounds[r].chunk_begin, ce = tab.rounds[r].chunk_end;
-          for (int s = 0; s < nslots; ++s) {
+          // lock-step: one pass over the round's chunks feeds every active slot; otherwise one pass per slot
+          const int passes = lockstep ? 1 : nslots;
+          for (int s = 0; s < passes; ++s) {
             if (nslots * pair + s >= n_tiles) continue;
             for (int c = cb; c < ce; ++c) {
               MCF_T0(tw);
@@ -307,11 +311,17 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
       for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int r = 0; r < p.n_rounds; ++r) {
           const int cb = tab.rounds[r].chunk_begin, ce = tab.rounds[r].chunk_end;
-          for (int s = 0; s < nslots; ++s) {
-            if (nslots * pair + s >= n_tiles) continue;
+          const int passes = lockstep ? 1 : nslots;
+          for (int s0 = 0; s0 < passes; ++s0) {
+            if (nslots * pair + s0 >= n_tiles) continue;
+            // slots fed by this pass over the weight chunks
+            const int s_lo = lockstep ? 0 : s0;
+            const int s_hi = lockstep ? ((nslots * pair + 1 < n_tiles) ? nslots : 1) : s0 + 1;
             MCF_T0(tm);
-            mbar_wait(&tab.act_ready[s], ar_phase[s], 0x200u | s);
-            ar_phase[s] ^= 1u;
+            for (int s = s_lo; s < s_hi; ++s) {
+              mbar_wait(&tab.act_ready[s], ar_phase[s], 0x200u | s);
+              ar_phase[s] ^= 1u;
+            }
             tc_fence_after();
             MCF_TACC(0, tm);
             for (int c = cb; c < ce; ++c) {
@@ -323,14 +333,19 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
               if (fuse) mbar_wait(&tab.w_full[stage + 1], phase, 0x300u | (stage + 1));
               tc_fence_after();
               MCF_TACC(1, tm);
-              const uint32_t a_base = (ch.a_buf ? (h_addr + s * L::kHBytes) : (x0_addr + s * kBlk)) + ch.a_kblock * kBlk;
               const uint32_t b_base = smem_base_addr + stage_off(stage);
               const uint32_t idesc = make_idesc(fuse ? 2u * ch.n : (uint32_t)ch.n);
-              const uint32_t d_tmem = tmem_base + s * kSlotCols + ch.acc_col;
-              for (uint32_t k = 0; k < ch.ksteps; ++k) {
-                const uint64_t ad = make_sdesc(a_base + k * 32u, 0u, 1024u);
-                const uint64_t bd = make_sdesc(b_base + k * 32u, 0u, 1024u);
-                umma_bf16(d_tmem, ad, bd, idesc, (k > 0u || !(ch.flags & 1u)) ? 1u : 0u);
+              for (int s = s_lo; s < s_hi; ++s) {
+                const uint32_t a_base =
+                    (ch.a_buf ? (h_addr + s * L::kHBytes) : (x0_addr + s * kBlk)) + ch.a_kblock * kBlk;
+                const uint32_t d_tmem = tmem_base + s * kSlotCols + ch.acc_col;
+                for (uint32_t k = 0; k < ch.ksteps; ++k) {
+                  const uint64_t ad = make_sdesc(a_base + k * 32u, 0u, 1024u);
+                  const uint64_t bd = make_sdesc(b_base + k * 32u, 0u, 1024u);
+                  umma_bf16(d_tmem, ad, bd, idesc, (k > 0u || !(ch.flags & 1u)) ? 1u : 0u);
+                }
+                // the first slot's accumulator is complete one slot-pass earlier than the last one's
+                if (c + (fuse ? 2 : 1) >= ce) umma_commit(&tab.acc_full[s]);
               }
               umma_commit(&tab.w_empty[stage]);
               if (++stage == nstages) { stage = 0; phase ^= 1u; }
@@ -341,7 +356,6 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
               }
               MCF_TACC(2, tm);
             }
-            umma_commit(&tab.acc_full[s]);
           }
         }
       }
@@ -353,9 +367,7 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
     }
   }
   } else {
-    // 256-wide: 128*72 + 256*208 <= 64K registers; 128-wide (three slots): 128*56 + 384*152 = 64K
-    if (W == 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;\n");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");   // 128*72 + 256*208 <= 64K registers
     // =========================== epilogue groups ===========================
     const int s = (warp - 4) >> 2;          // slot
     const int qtr = warp & 3;               // TMEM lane quarter this warp may access
