@@ -23,27 +23,21 @@
 
 namespace mcf {
 
-constexpr int kMaxSlots = 4;
-// tiles in flight per CTA (three for the 128-wide chain was measured slower: the MMA issue rate dropped)
-template <int W> struct Cfg {
-  static constexpr int kSlots = 2;
-  static constexpr int kThreads = 128 + 128 * kSlots;
-  static constexpr uint32_t kSlotCols = (W == 128) ? 128u : 256u;   // TMEM columns per slot
-};
-constexpr int kStages = 4;      // ring stages in the dedicated ring region
-constexpr int kMaxStages = 8;   // single-slot mode adds the idle slot's activation buffer as four more stages
+constexpr int kThreads = 384;
+constexpr int kStages = 4;
 constexpr uint32_t kBlk = MCF_BLOCK_BYTES;
-constexpr int kMaxChunks = 120;
+constexpr int kMaxChunks = 128;
 constexpr int kMaxRounds = 24;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr uint32_t kSlotCols = 256;
 
 struct Tables {
   mcf_chunk_t chunks[kMaxChunks];  // 2048 B
   mcf_round_t rounds[kMaxRounds];  // 768 B
-  uint64_t w_full[kMaxStages];
-  uint64_t w_empty[kMaxStages];
-  uint64_t act_ready[kMaxSlots];
-  uint64_t acc_full[kMaxSlots];
+  uint64_t w_full[kStages];
+  uint64_t w_empty[kStages];
+  uint64_t act_ready[2];
+  uint64_t acc_full[2];
   uint32_t tmem_base;
   uint32_t pad[3];
 };
@@ -52,14 +46,13 @@ template <int W>
 struct Smem {
   static constexpr uint32_t kHBlocks = W / 64;
   static constexpr uint32_t kHBytes = kHBlocks * kBlk;
-  static constexpr uint32_t kSlots = Cfg<W>::kSlots;
   static constexpr uint32_t off_h = 0;
-  static constexpr uint32_t off_x0 = off_h + kSlots * kHBytes;
-  static constexpr uint32_t off_ring = off_x0 + kSlots * kBlk;
+  static constexpr uint32_t off_x0 = off_h + 2 * kHBytes;
+  static constexpr uint32_t off_ring = off_x0 + 2 * kBlk;
   static constexpr uint32_t off_tab = off_ring + kStages * kBlk;
   static constexpr uint32_t total = off_tab + sizeof(Tables);
 };
-static_assert(Smem<256>::total <= 232448 && Smem<128>::total <= 232448, "shared memory budget exceeded");
+static_assert(Smem<256>::total <= 232448, "shared memory budget exceeded");
 
 // ---------------------------------------------------------------------------------------------
 // epilogue helpers (thread == row)
@@ -209,14 +202,10 @@ __device__ __forceinline__ void nof_quat_backward(const float* h9, const float* 
   do { if (timing) { long long _n = clock64(); tacc[slot] += (unsigned long long)(_n - var); var = _n; } } while (0)
 
 template <int W>
-__global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_constant__ mcf_chain_params_t p) {
-  constexpr int kThreads = Cfg<W>::kThreads;
-  constexpr int kSlots = Cfg<W>::kSlots;
-  constexpr uint32_t kSlotCols = Cfg<W>::kSlotCols;
+__global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ mcf_chain_params_t p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const bool timing = p.timing != nullptr;
   unsigned long long tacc[4] = {0ull, 0ull, 0ull, 0ull};
-  unsigned long long tfine[2] = {0ull, 0ull};
   const long long t_kernel0 = timing ? clock64() : 0;
   using L = Smem<W>;
   Tables& tab = *reinterpret_cast<Tables*>(smem + L::off_tab);
@@ -236,14 +225,14 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
     uint32_t* dst_r = reinterpret_cast<uint32_t*>(tab.rounds);
     for (int i = threadIdx.x; i < p.n_rounds * 8; i += kThreads) dst_r[i] = src_r[i];
     uint4* x0z = reinterpret_cast<uint4*>(smem + L::off_x0);
-    for (int i = threadIdx.x; i < (int)(kSlots * kBlk / 16); i += kThreads) x0z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (int)(2 * kBlk / 16); i += kThreads) x0z[i] = make_uint4(0, 0, 0, 0);
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kMaxStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&tab.w_full[s], 1);
       mbar_init(&tab.w_empty[s], 1);
     }
-    for (int s = 0; s < kMaxSlots; ++s) {
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&tab.act_ready[s], 128);
       mbar_init(&tab.acc_full[s], 1);
     }
@@ -260,16 +249,7 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
   const uint32_t tmem_base = tab.tmem_base;
 
   const long long n_tiles = (p.n_rows + MCF_TILE_ROWS - 1) / MCF_TILE_ROWS;
-  const int nslots = (W == 256 && p.n_slots == 1) ? 1 : kSlots;
-  const long long n_pairs = (n_tiles + nslots - 1) / nslots;   // groups of nslots tiles
-  const uint32_t nstages = nslots == 1 ? (uint32_t)kMaxStages : (uint32_t)kStages;
-  // n_slots == 3: both slots run the same layer at the same time and share every weight chunk (half the weight
-  // traffic per FLOP, no ping-pong between the tensor core and the epilogues)
-  const bool lockstep = p.n_slots == 3 && nslots == 2;
-  // byte offset of ring stage `st`: the ring region, then (single-slot mode) the unused slot-1 activation buffer
-  auto stage_off = [&](uint32_t st) -> uint32_t {
-    return st < (uint32_t)kStages ? L::off_ring + st * kBlk : L::off_h + L::kHBytes + (st - (uint32_t)kStages) * kBlk;
-  };
+  const long long n_pairs = (n_tiles + 1) / 2;
 
   // register re-distribution between the warpgroups: the producer/MMA/allocator warpgroup needs few registers,
   // the two epilogue warpgroups hold 64 accumulator + 64 bias values in flight (128*72 + 256*208 <= 64K)
@@ -283,18 +263,16 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
       for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int r = 0; r < p.n_rounds; ++r) {
           const int cb = tab.rounds[r].chunk_begin, ce = tab.rounds[r].chunk_end;
-          // lock-step: one pass over the round's chunks feeds every active slot; otherwise one pass per slot
-          const int passes = lockstep ? 1 : nslots;
-          for (int s = 0; s < passes; ++s) {
-            if (nslots * pair + s >= n_tiles) continue;
+          for (int s = 0; s < 2; ++s) {
+            if (2 * pair + s >= n_tiles) continue;
             for (int c = cb; c < ce; ++c) {
               MCF_T0(tw);
               mbar_wait(&tab.w_empty[stage], phase ^ 1u, 0x100u | stage);
               MCF_TACC(0, tw);
               const uint32_t bytes = tab.chunks[c].bytes;
               mbar_arrive_expect_tx(&tab.w_full[stage], bytes);
-              bulk_g2s(smem + stage_off(stage), wsrc + tab.chunks[c].src_off, bytes, &tab.w_full[stage]);
-              if (++stage == nstages) { stage = 0; phase ^= 1u; }
+              bulk_g2s(smem + L::off_ring + stage * kBlk, wsrc + tab.chunks[c].src_off, bytes, &tab.w_full[stage]);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
           }
         }
@@ -305,23 +283,17 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      uint32_t ar_phase[kMaxSlots] = {0u, 0u, 0u, 0u};
+      uint32_t ar_phase[2] = {0u, 0u};
       const uint32_t h_addr = smem_u32(smem + L::off_h), x0_addr = smem_u32(smem + L::off_x0);
-      const uint32_t smem_base_addr = smem_u32(smem);
+      const uint32_t ring_addr = smem_u32(smem + L::off_ring);
       for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int r = 0; r < p.n_rounds; ++r) {
           const int cb = tab.rounds[r].chunk_begin, ce = tab.rounds[r].chunk_end;
-          const int passes = lockstep ? 1 : nslots;
-          for (int s0 = 0; s0 < passes; ++s0) {
-            if (nslots * pair + s0 >= n_tiles) continue;
-            // slots fed by this pass over the weight chunks
-            const int s_lo = lockstep ? 0 : s0;
-            const int s_hi = lockstep ? ((nslots * pair + 1 < n_tiles) ? nslots : 1) : s0 + 1;
+          for (int s = 0; s < 2; ++s) {
+            if (2 * pair + s >= n_tiles) continue;
             MCF_T0(tm);
-            for (int s = s_lo; s < s_hi; ++s) {
-              mbar_wait(&tab.act_ready[s], ar_phase[s], 0x200u | s);
-              ar_phase[s] ^= 1u;
-            }
+            mbar_wait(&tab.act_ready[s], ar_phase[s], 0x200u | s);
+            ar_phase[s] ^= 1u;
             tc_fence_after();
             MCF_TACC(0, tm);
             for (int c = cb; c < ce; ++c) {
@@ -333,29 +305,25 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
               if (fuse) mbar_wait(&tab.w_full[stage + 1], phase, 0x300u | (stage + 1));
               tc_fence_after();
               MCF_TACC(1, tm);
-              const uint32_t b_base = smem_base_addr + stage_off(stage);
+              const uint32_t a_base = (ch.a_buf ? (h_addr + s * L::kHBytes) : (x0_addr + s * kBlk)) + ch.a_kblock * kBlk;
+              const uint32_t b_base = ring_addr + stage * kBlk;
               const uint32_t idesc = make_idesc(fuse ? 2u * ch.n : (uint32_t)ch.n);
-              for (int s = s_lo; s < s_hi; ++s) {
-                const uint32_t a_base =
-                    (ch.a_buf ? (h_addr + s * L::kHBytes) : (x0_addr + s * kBlk)) + ch.a_kblock * kBlk;
-                const uint32_t d_tmem = tmem_base + s * kSlotCols + ch.acc_col;
-                for (uint32_t k = 0; k < ch.ksteps; ++k) {
-                  const uint64_t ad = make_sdesc(a_base + k * 32u, 0u, 1024u);
-                  const uint64_t bd = make_sdesc(b_base + k * 32u, 0u, 1024u);
-                  umma_bf16(d_tmem, ad, bd, idesc, (k > 0u || !(ch.flags & 1u)) ? 1u : 0u);
-                }
-                // the first slot's accumulator is complete one slot-pass earlier than the last one's
-                if (c + (fuse ? 2 : 1) >= ce) umma_commit(&tab.acc_full[s]);
+              const uint32_t d_tmem = tmem_base + s * kSlotCols + ch.acc_col;
+              for (uint32_t k = 0; k < ch.ksteps; ++k) {
+                const uint64_t ad = make_sdesc(a_base + k * 32u, 0u, 1024u);
+                const uint64_t bd = make_sdesc(b_base + k * 32u, 0u, 1024u);
+                umma_bf16(d_tmem, ad, bd, idesc, (k > 0u || !(ch.flags & 1u)) ? 1u : 0u);
               }
               umma_commit(&tab.w_empty[stage]);
-              if (++stage == nstages) { stage = 0; phase ^= 1u; }
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
               if (fuse) {
                 umma_commit(&tab.w_empty[stage]);
-                if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 ++c;
               }
               MCF_TACC(2, tm);
             }
+            umma_commit(&tab.acc_full[s]);
           }
         }
       }
@@ -367,7 +335,7 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");   // 128*72 + 256*208 <= 64K registers
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");
     // =========================== epilogue groups ===========================
     const int s = (warp - 4) >> 2;          // slot
     const int qtr = warp & 3;               // TMEM lane quarter this warp may access
@@ -381,8 +349,7 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
     bool store_pending = false;
 
     for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      if (s >= nslots) break;
-      const long long tile = nslots * pair + s;
+      const long long tile = 2 * pair + s;
       if (tile >= n_tiles) break;
       const long long m = tile * MCF_TILE_ROWS + row;
       const bool valid = m < p.n_rows;
@@ -612,19 +579,14 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
           tmem_ld32(t_acc, va);
           for (int c0 = 0; c0 < rd.n_out; c0 += 64) {
             load32f(bias_p + c0 + 32, b1);
-            long long tq = timing ? clock64() : 0;
             tmem_ld_wait();
-            if (timing) { long long n = clock64(); tfine[0] += (unsigned long long)(n - tq); tq = n; }
             tmem_ld32(t_acc + c0 + 32, vb);
             do_chunk(c0, va, b0);
-            if (timing) { long long n = clock64(); tfine[1] += (unsigned long long)(n - tq); tq = n; }
             const bool more = c0 + 64 < rd.n_out;
             if (more) load32f(bias_p + c0 + 64, b0);
             tmem_ld_wait();
-            if (timing) { long long n = clock64(); tfine[0] += (unsigned long long)(n - tq); tq = n; }
             if (more) tmem_ld32(t_acc + c0 + 64, va);
             do_chunk(c0 + 32, vb, b1);
-            if (timing) { long long n = clock64(); tfine[1] += (unsigned long long)(n - tq); }
           }
           if (rd.epi == MCF_EPI_RELU_SIGMA) {
             st.sigma = sig + __ldg(p.consts + rd.aux_off + rd.n_out);
@@ -771,7 +733,6 @@ __global__ void __launch_bounds__(Cfg<W>::kThreads, 1) k_chain(const __grid_cons
     if (timing && gtid == 0) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) p.timing[blockIdx.x * 16 + s * 4 + j] = tacc[j];
-      if (s == 0) { p.timing[blockIdx.x * 16 + 13] = tfine[0]; p.timing[blockIdx.x * 16 + 14] = tfine[1]; }
     }
   }
 
@@ -947,8 +908,7 @@ int mcf_chain_launch(const mcf_chain_params_t* pp, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
   }
   long long n_tiles = (p.n_rows + MCF_TILE_ROWS - 1) / MCF_TILE_ROWS;
-  const int nslots = (p.width == 256 && p.n_slots == 1) ? 1 : (p.width == 128 ? mcf::Cfg<128>::kSlots : mcf::Cfg<256>::kSlots);
-  long long n_pairs = (n_tiles + nslots - 1) / nslots;
+  long long n_pairs = (n_tiles + 1) / 2;
   int cap = p.max_ctas > 0 ? p.max_ctas : n_sm;
   int grid = (int)(n_pairs < cap ? n_pairs : cap);
   cudaError_t e;
@@ -956,12 +916,12 @@ int mcf_chain_launch(const mcf_chain_params_t* pp, cudaStream_t stream) {
     const int smem = (int)mcf::Smem<256>::total;
     e = cudaFuncSetAttribute(mcf::k_chain<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    mcf::k_chain<256><<<grid, mcf::Cfg<256>::kThreads, smem, stream>>>(p);
+    mcf::k_chain<256><<<grid, mcf::kThreads, smem, stream>>>(p);
   } else if (p.width == 128) {
     const int smem = (int)mcf::Smem<128>::total;
     e = cudaFuncSetAttribute(mcf::k_chain<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    mcf::k_chain<128><<<grid, mcf::Cfg<128>::kThreads, smem, stream>>>(p);
+    mcf::k_chain<128><<<grid, mcf::kThreads, smem, stream>>>(p);
   } else {
     return MCF_ERR_UNSUPPORTED;
   }

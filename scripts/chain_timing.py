@@ -12,7 +12,7 @@ import moco_flow_b200 as mf  # noqa: E402
 from moco_flow_b200 import ops  # noqa: E402
 
 NAMES = ["s0 prologue", "s0 wait acc", "s0 epilogue", "s0 save/bar", "s1 prologue", "s1 wait acc", "s1 epilogue",
-         "s1 save/bar", "mma wait act", "mma wait w", "mma issue", "prod wait ring", "total", "s0 ldtm wait", "s0 chunk math"]
+         "s1 save/bar", "mma wait act", "mma wait w", "mma issue", "prod wait ring", "total"]
 
 
 def main():
@@ -43,11 +43,11 @@ def main():
         print(f"=== {name} ===")
         for tag, bufs in timing.items():
             for i, b in enumerate(bufs):
-                t = b[:148, :15].double().cpu()
+                t = b[:148, :13].double().cpu()
                 active = t[:, 12] > 0
                 m = t[active].mean(0)
                 tot = m[12].item()
-                parts = "  ".join(f"{n}={100*v/tot:4.1f}%" for n, v in zip(NAMES[:12] + NAMES[13:], m[:12].tolist() + m[13:15].tolist()))
+                parts = "  ".join(f"{n}={100*v/tot:4.1f}%" for n, v in zip(NAMES[:12], m[:12].tolist()))
                 print(f"{tag}[{i}] ctas={int(active.sum())} total={tot/1e3:.0f}k cyc | {parts}")
 
 
