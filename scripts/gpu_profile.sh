@@ -36,7 +36,7 @@ timeout 900 ncu --set full --clock-control none -k regex:k_chain -s 82 -c 4 \
     > gpurun_out/ncu_chain_train_$R.log 2>&1
 export_rep prof_chain_train_$R
 # 4. weight-gradient GEMM: first launches of the 4th step's backward (fine NeRF layers)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_dw -s 264 -c 3 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_dw -s 36 -c 3 \
     -o gpurun_out/prof_dw_$R -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph \
     > gpurun_out/ncu_dw_$R.log 2>&1
 export_rep prof_dw_$R source
