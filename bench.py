@@ -147,6 +147,9 @@ def run_ours(args):
     dp.broadcast_parameters(nerfs + nofs)
     train = args.workload == "train"
     R = RAYS_PER_GPU
+    if args.workload == "frame":  # 540 x 540 pixels, contiguous ray ranges per GPU (strong scaling)
+        b, e = dp.shard_bounds(540 * 540, rank, world)
+        R = e - b
     # this rank's shard of the step's global batch (N * 4096 rays): weak scaling
     rays_h, bg_h, tgt_h = synth_batch(R, seed=1 + rank)
     rays_h, bg_h, tgt_h = rays_h.pin_memory(), bg_h.pin_memory(), tgt_h.pin_memory()
@@ -288,7 +291,7 @@ def run_ours(args):
     tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json: sustained bf16, copy HBM)" if peaks else "fallback (B200_PROFILING.md)"
-    total_rays = world * R * args.steps
+    total_rays = (540 * 540 if args.workload == "frame" else world * R) * args.steps
     kernels = {}
     for tag, d in agg.items():
         rate = d["work"] / (d["ms"] * 1e-3) if d["ms"] > 0 else 0.0
@@ -330,16 +333,20 @@ def run_ours(args):
                "ms_per_step": round(tm / 2, 4)}
         best = max(chain_tags, key=lambda t: agg[t]["work"] / max(agg[t]["ms"], 1e-9))
         mlp["best_kernel"] = roof(best)
-    flops_ray = algorithmic_flops_per_ray(args.workload)
+    flops_ray = algorithmic_flops_per_ray("train" if train else "render")
     h2d = int(rays_h.numel() + bg_h.numel() + tgt_h.numel()) * 4
     line = {
         "metric": "train rays/s (fwd+bwd, 64+64 spp)" if train else "render rays/s (64+64 spp, test_time)",
         "value": round(total_rays / (ms * 1e-3), 1), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "strong" if args.workload == "frame" else "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
         "config": {"workload": ("MoCo-Flow training step fwd+bwd (BASELINE configs[2]): 4096 rays/GPU, 64+64 samples, "
                                 "bw/fw NoF chains (local+global), random-init c2f.yaml shapes, Adam step, "
                                 "ray-sharded DP + flat-gradient NCCL all-reduce") if train else
+                               ("full-frame inference render (BASELINE configs[3] shape): 540x540 rays per step "
+                                "sharded over the GPUs, 64+64 samples, test_time; ms_per_step = ms/frame")
+                               if args.workload == "frame" else
                                ("full MoCo-Flow ray render (BASELINE configs[1]): 4096 rays, 64+64 samples, test_time"),
                    "rays_per_gpu": R, "n_coarse": N_COARSE, "n_fine": N_FINE,
                    "l2": "no flush: the step streams > 5 GB of saved operand images per GPU, far above the 126 MB L2",
@@ -455,7 +462,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "render"])
+    ap.add_argument("--workload", default="train", choices=["train", "render", "frame"],
+                    help="train: configs[2] step; render: configs[1] 4096-ray render; frame: one 540x540 frame "
+                         "(configs[3] shape) per step, rays sharded over the GPUs")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
