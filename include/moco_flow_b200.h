@@ -203,9 +203,9 @@ typedef struct {
    * 0-3 slot0 {prologue, wait acc_full, epilogue, save/barrier}, 4-7 slot1, 8 MMA wait act_ready,
    * 9 MMA wait weights, 10 MMA issue, 11 producer wait ring, 12 total */
   unsigned long long* timing;
-  /* 0/2: two tiles per CTA ping-pong (4-stage weight ring); 1: one tile per CTA and the second tile's buffers
-   * become four more ring stages (width 256 only) -- trades the ping-pong for weight-prefetch depth */
-  int32_t n_slots;
+  /* width 256 only: non-zero launches clusters of two CTAs that run tcgen05 cta_group::2 (one M=256 MMA stream over
+   * both CTAs' tiles; every CTA fetches only its half of each weight chunk) */
+  int32_t cta_pair;
 } mcf_chain_params_t;
 
 int mcf_chain_launch(const mcf_chain_params_t* params_host, cudaStream_t stream);

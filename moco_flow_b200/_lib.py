@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmoco_flow_b200.so")
+LIB_PATH = os.environ.get("MCF_LIB_PATH") or os.path.join(_HERE, "csrc", "libmoco_flow_b200.so")  # override: kernel experiments only
 
 MAX_FREQS = 24
 TILE_ROWS = 128
@@ -56,7 +56,7 @@ class ChainParams(C.Structure):
         ("fwd_mask_tile_words", _i64), ("fwd_x0_off", _u32), ("fwd_he_off", _u32),
         ("d_xyz", _vp), ("d_head", _vp), ("rayfeat", _vp), ("rayfeat_stride", _i32), ("rayfeat_dim", _i32),
         ("extra_save_off", _u32), ("dhead_save_off", _u32), ("max_ctas", _i32),
-        ("timing", _vp), ("n_slots", _i32),
+        ("timing", _vp), ("cta_pair", _i32),
     ]
 
 

@@ -24,7 +24,8 @@
 namespace mcf {
 
 constexpr int kThreads = 384;
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;
+constexpr int kProducers = 1;  // producer warps (0, then 2, 3).  More than one was measured: no gain, their polling costs issue slots
 constexpr uint32_t kBlk = MCF_BLOCK_BYTES;
 constexpr int kMaxChunks = 128;
 constexpr int kMaxRounds = 24;
@@ -34,8 +35,9 @@ constexpr uint32_t kSlotCols = 256;
 struct Tables {
   mcf_chunk_t chunks[kMaxChunks];  // 2048 B
   mcf_round_t rounds[kMaxRounds];  // 768 B
-  uint64_t w_full[kStages];
-  uint64_t w_empty[kStages];
+  uint64_t w_full[kMaxStages];
+  uint64_t w_empty[kMaxStages];
+  uint64_t w_peer[kMaxStages];  // CTA pairs: the peer's half of a ring stage has landed (leader CTA only)
   uint64_t act_ready[2];
   uint64_t acc_full[2];
   uint32_t tmem_base;
@@ -44,6 +46,7 @@ struct Tables {
 
 template <int W>
 struct Smem {
+  static constexpr int kStages = 4;   // 16 KB weight-ring stages.  8 at W=128 measured slower: the larger carve-out shrinks L1
   static constexpr uint32_t kHBlocks = W / 64;
   static constexpr uint32_t kHBytes = kHBlocks * kBlk;
   static constexpr uint32_t off_h = 0;
@@ -52,7 +55,7 @@ struct Smem {
   static constexpr uint32_t off_tab = off_ring + kStages * kBlk;
   static constexpr uint32_t total = off_tab + sizeof(Tables);
 };
-static_assert(Smem<256>::total <= 232448, "shared memory budget exceeded");
+static_assert(Smem<256>::total <= 232448 && Smem<128>::total <= 232448, "shared memory budget exceeded");
 
 // ---------------------------------------------------------------------------------------------
 // epilogue helpers (thread == row)
@@ -76,6 +79,11 @@ __device__ __forceinline__ void store_h32(uint8_t* hbuf, uint32_t row, uint32_t 
 }
 
 __device__ __forceinline__ void load32f(const float* __restrict__ p, float (&b)[32]) {
+#ifdef MCF_EXP_NOBIAS
+#pragma unroll
+  for (int q = 0; q < 32; ++q) b[q] = 0.25f;
+  return;
+#endif
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
@@ -201,15 +209,20 @@ __device__ __forceinline__ void nof_quat_backward(const float* h9, const float* 
 #define MCF_TACC(slot, var) \
   do { if (timing) { long long _n = clock64(); tacc[slot] += (unsigned long long)(_n - var); var = _n; } } while (0)
 
-template <int W>
+// C = CTAs per cluster.  C == 2: the two CTAs of a pair run tcgen05 cta_group::2 -- the leader's MMA thread issues
+// M=256 instructions over both CTAs' tiles, every CTA streams only its half of each weight chunk (the N split of
+// the B operand), which halves the L2 -> shared-memory weight traffic per tile and doubles the ring's depth in time.
+template <int W, int C>
 __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ mcf_chain_params_t p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const bool timing = p.timing != nullptr;
   unsigned long long tacc[4] = {0ull, 0ull, 0ull, 0ull};
   const long long t_kernel0 = timing ? clock64() : 0;
   using L = Smem<W>;
+  constexpr int kStages = L::kStages;
   Tables& tab = *reinterpret_cast<Tables*>(smem + L::off_tab);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (C == 2) ? cluster_ctarank() : 0u;
 
   if ((smem_u32(smem) & 1023u) != 0u) {
     if (threadIdx.x == 0) atomicExch(&g_mcf_device_error, 0xA11C0000u);
@@ -231,68 +244,117 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&tab.w_full[s], 1);
       mbar_init(&tab.w_empty[s], 1);
+      mbar_init(&tab.w_peer[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&tab.act_ready[s], 128);
+      mbar_init(&tab.act_ready[s], C == 2 ? 8 : 128);  // pairs: one arrival per epilogue warp of both CTAs, on the leader's barrier
       mbar_init(&tab.acc_full[s], 1);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(&tab.tmem_base, 512);
-    tmem_relinquish();
+    if (C == 2) {
+      tmem_alloc_pair(&tab.tmem_base, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(&tab.tmem_base, 512);
+      tmem_relinquish();
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (C == 2) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = tab.tmem_base;
 
+  // work units: a unit is 2 slots x C CTAs = 2C consecutive tiles; tile(u, s) = (2u + s) * C + cta_rank.
+  // C == 1 skips a slot whose tile does not exist; a pair runs missing tiles as all-invalid rows so that both
+  // CTAs walk identical weight / barrier sequences.
   const long long n_tiles = (p.n_rows + MCF_TILE_ROWS - 1) / MCF_TILE_ROWS;
-  const long long n_pairs = (n_tiles + 1) / 2;
+  const long long n_pairs = (n_tiles + 2 * C - 1) / (2 * C);
+  const long long unit0 = blockIdx.x / C, unit_step = gridDim.x / C;
+  auto tile_of = [&](long long u, int s) -> long long { return (2 * u + s) * C + cta_rank; };
+  auto wait_x = [&](uint64_t* bar, uint32_t parity, uint32_t tag) {
+    if (C == 2) mbar_wait_cluster(bar, parity, tag); else mbar_wait(bar, parity, tag);
+  };
 
   // register re-distribution between the warpgroups: the producer/MMA/allocator warpgroup needs few registers,
   // the two epilogue warpgroups hold 64 accumulator + 64 bias values in flight (128*72 + 256*208 <= 64K)
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
-  if (warp == 0) {
-    // =========================== weight producer ===========================
-    if (lane == 0) {
+  if (warp != 1) {
+    // =========================== weight producers (warps 0, 2, 3) ===========================
+    // Every producer walks the whole copy sequence (to track stage / phase) and issues every kProducers-th copy.
+    const int me = (warp == 0) ? 0 : warp - 1;
+    if (lane == 0 && me < kProducers) {
+      int turn = 0;
       uint32_t stage = 0, phase = 0;
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack);
-      for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      for (long long pair = unit0; pair < n_pairs; pair += unit_step) {
         for (int r = 0; r < p.n_rounds; ++r) {
           const int cb = tab.rounds[r].chunk_begin, ce = tab.rounds[r].chunk_end;
           for (int s = 0; s < 2; ++s) {
-            if (2 * pair + s >= n_tiles) continue;
+            if (C == 1 && tile_of(pair, s) >= n_tiles) continue;
             for (int c = cb; c < ce; ++c) {
-              MCF_T0(tw);
-              mbar_wait(&tab.w_empty[stage], phase ^ 1u, 0x100u | stage);
-              MCF_TACC(0, tw);
-              const uint32_t bytes = tab.chunks[c].bytes;
-              mbar_arrive_expect_tx(&tab.w_full[stage], bytes);
-              bulk_g2s(smem + L::off_ring + stage * kBlk, wsrc + tab.chunks[c].src_off, bytes, &tab.w_full[stage]);
+              uint32_t bytes = tab.chunks[c].bytes, src_off = tab.chunks[c].src_off;
+              if (C == 2) {
+                if (tab.chunks[c].flags & 2u) {   // [256 x 64] weight tile: this CTA's 128-row half is one chunk
+                  bytes = tab.chunks[c + cta_rank].bytes;
+                  src_off = tab.chunks[c + cta_rank].src_off;
+                  ++c;
+                } else {                          // single chunk: this CTA's half of its rows
+                  bytes >>= 1;
+                  src_off += cta_rank * bytes;
+                }
+              }
+              if (turn == me) {
+                MCF_T0(tw);
+                wait_x(&tab.w_empty[stage], phase ^ 1u, 0x100u | stage);
+                MCF_TACC(0, tw);
+                mbar_arrive_expect_tx(&tab.w_full[stage], bytes);
+                bulk_g2s(smem + L::off_ring + stage * kBlk, wsrc + src_off, bytes, &tab.w_full[stage]);
+              }
+              if (++turn == kProducers) turn = 0;
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
           }
         }
       }
-      if (timing) p.timing[blockIdx.x * 16 + 11] = tacc[0];
+      if (timing && me == 0) p.timing[blockIdx.x * 16 + 11] = tacc[0];
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    if (lane == 0 && C == 2 && cta_rank != 0u) {
+      // ---- peer CTA of a pair: relay "my half of the stage has landed" to the leader's MMA thread ----
+      uint32_t stage = 0, phase = 0;
+      uint32_t peer_bar[kStages];
+      for (int i = 0; i < kStages; ++i) peer_bar[i] = map_to_cta(smem_u32(&tab.w_peer[i]), 0u);
+      for (long long pair = unit0; pair < n_pairs; pair += unit_step) {
+        for (int r = 0; r < p.n_rounds; ++r) {
+          const int cb = tab.rounds[r].chunk_begin, ce = tab.rounds[r].chunk_end;
+          for (int s = 0; s < 2; ++s) {
+            for (int c = cb; c < ce; ++c) {
+              if (tab.chunks[c].flags & 2u) ++c;
+              mbar_wait(&tab.w_full[stage], phase, 0x500u | stage);
+              mbar_arrive_cluster(peer_bar[stage]);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       uint32_t ar_phase[2] = {0u, 0u};
       const uint32_t h_addr = smem_u32(smem + L::off_h), x0_addr = smem_u32(smem + L::off_x0);
       const uint32_t ring_addr = smem_u32(smem + L::off_ring);
-      for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      for (long long pair = unit0; pair < n_pairs; pair += unit_step) {
         for (int r = 0; r < p.n_rounds; ++r) {
           const int cb = tab.rounds[r].chunk_begin, ce = tab.rounds[r].chunk_end;
           for (int s = 0; s < 2; ++s) {
-            if (2 * pair + s >= n_tiles) continue;
+            if (C == 1 && tile_of(pair, s) >= n_tiles) continue;
             MCF_T0(tm);
-            mbar_wait(&tab.act_ready[s], ar_phase[s], 0x200u | s);
+            wait_x(&tab.act_ready[s], ar_phase[s], 0x200u | s);
             ar_phase[s] ^= 1u;
             tc_fence_after();
             MCF_TACC(0, tm);
@@ -302,28 +364,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
               // flag bit1: this chunk and the next one are the two 128-row halves of one [256 x 64] weight tile
               // sitting in consecutive (even, odd) ring stages -> one N=256 instruction per K step
               const bool fuse = (ch.flags & 2u) != 0u;
-              if (fuse) mbar_wait(&tab.w_full[stage + 1], phase, 0x300u | (stage + 1));
+              if (C == 2) mbar_wait_cluster(&tab.w_peer[stage], phase, 0x600u | stage);
+              else if (fuse) mbar_wait(&tab.w_full[stage + 1], phase, 0x300u | (stage + 1));
               tc_fence_after();
               MCF_TACC(1, tm);
               const uint32_t a_base = (ch.a_buf ? (h_addr + s * L::kHBytes) : (x0_addr + s * kBlk)) + ch.a_kblock * kBlk;
               const uint32_t b_base = ring_addr + stage * kBlk;
-              const uint32_t idesc = make_idesc(fuse ? 2u * ch.n : (uint32_t)ch.n);
+              const uint32_t idesc = make_idesc(fuse ? 2u * ch.n : (uint32_t)ch.n, false, false, 128u * C);
               const uint32_t d_tmem = tmem_base + s * kSlotCols + ch.acc_col;
               for (uint32_t k = 0; k < ch.ksteps; ++k) {
                 const uint64_t ad = make_sdesc(a_base + k * 32u, 0u, 1024u);
                 const uint64_t bd = make_sdesc(b_base + k * 32u, 0u, 1024u);
-                umma_bf16(d_tmem, ad, bd, idesc, (k > 0u || !(ch.flags & 1u)) ? 1u : 0u);
+                if (C == 2) umma_bf16_pair(d_tmem, ad, bd, idesc, (k > 0u || !(ch.flags & 1u)) ? 1u : 0u);
+                else umma_bf16(d_tmem, ad, bd, idesc, (k > 0u || !(ch.flags & 1u)) ? 1u : 0u);
               }
-              umma_commit(&tab.w_empty[stage]);
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
-              if (fuse) {
+              if (C == 2) {
+                umma_commit_pair(&tab.w_empty[stage], 3);   // frees the stage in both CTAs
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                if (fuse) ++c;
+              } else {
                 umma_commit(&tab.w_empty[stage]);
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                ++c;
+                if (fuse) {
+                  umma_commit(&tab.w_empty[stage]);
+                  if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                  ++c;
+                }
               }
               MCF_TACC(2, tm);
             }
-            umma_commit(&tab.acc_full[s]);
+            if (C == 2) umma_commit_pair(&tab.acc_full[s], 3);
+            else umma_commit(&tab.acc_full[s]);
           }
         }
       }
@@ -344,13 +415,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     uint8_t* hbuf = smem + L::off_h + s * L::kHBytes;
     uint8_t* x0buf = smem + L::off_x0 + s * kBlk;
     const uint32_t t_row = tmem_base + ((uint32_t)(qtr * 32) << 16) + s * kSlotCols;
-    const bool saving = p.save != nullptr;
+    const uint32_t act_ready_leader = (C == 2) ? map_to_cta(smem_u32(&tab.act_ready[s]), 0u) : 0u;
+    auto arrive_act_ready = [&]() {
+      if (C == 2) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(act_ready_leader);
+      } else {
+        mbar_arrive(&tab.act_ready[s]);
+      }
+    };
     uint32_t af_phase = 0;
     bool store_pending = false;
 
-    for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const long long tile = 2 * pair + s;
-      if (tile >= n_tiles) break;
+    for (long long pair = unit0; pair < n_pairs; pair += unit_step) {
+      const long long tile = tile_of(pair, s);
+      if (C == 1 && tile >= n_tiles) break;
+      const bool tile_ok = tile < n_tiles;                     // false: a pair's padding tile (no loads/stores)
+      const long long tile_r = tile_ok ? tile : n_tiles - 1;   // tile index for reads
+      const bool saving = p.save != nullptr && tile_ok;
       const long long m = tile * MCF_TILE_ROWS + row;
       const bool valid = m < p.n_rows;
       const long long mc = valid ? m : (p.n_rows - 1);
@@ -439,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         const mcf_round_t& r0 = tab.rounds[0];
         const int nhe = W / 2;
         const float* wrgb = p.consts + r0.aux_off;  // [3][W/2]
-        const uint32_t* mk = p.fwd_masks + tile * p.fwd_mask_tile_words + r0.mask_off;
+        const uint32_t* mk = p.fwd_masks + tile_r * p.fwd_mask_tile_words + r0.mask_off;
         for (int c0 = 0; c0 < nhe; c0 += 32) {
           float w0[32], w1[32], w2[32], f[32];
           load32f(wrgb + c0, w0);
@@ -518,7 +600,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         }
         store_pending = true;
       }
-      mbar_arrive(&tab.act_ready[s]);
+      arrive_act_ready();
       MCF_TACC(0, te);
 
       // ------------------------------- rounds -------------------------------
@@ -532,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         uint32_t mwords[8];
         if (is_bias_epi) load32f(bias_p, b0);
         if (is_mask_epi && rd.mask_off != kNone) {
-          const uint32_t* mkp = p.fwd_masks + tile * p.fwd_mask_tile_words + rd.mask_off + row;
+          const uint32_t* mkp = p.fwd_masks + tile_r * p.fwd_mask_tile_words + rd.mask_off + row;
 #pragma unroll
           for (int j = 0; j < 8; ++j) mwords[j] = (j * 32 < rd.n_out) ? __ldg(mkp + j * 128) : 0u;
         } else {
@@ -540,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           for (int j = 0; j < 8; ++j) mwords[j] = 0xFFFFFFFFu;
         }
         MCF_TACC(2, te);
-        mbar_wait(&tab.acc_full[s], af_phase, 0x400u | s);
+        wait_x(&tab.acc_full[s], af_phase, 0x400u | s);
         af_phase ^= 1u;
         tc_fence_after();
         MCF_TACC(1, te);
@@ -554,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         const uint32_t t_acc = t_row + rd.acc_col;
 
         if (rd.epi == MCF_EPI_RELU || rd.epi == MCF_EPI_RELU_SIGMA || rd.epi == MCF_EPI_LINEAR) {
-          const bool want_mask = p.masks != nullptr && rd.mask_off != kNone;
+          const bool want_mask = p.masks != nullptr && rd.mask_off != kNone && tile_ok;
           uint32_t* mk = want_mask ? (p.masks + tile * p.mask_tile_words + rd.mask_off + row) : nullptr;
           float sig = 0.f;
           float b1[32];
@@ -619,7 +701,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
 #pragma unroll
             for (int j = 0; j < 32; ++j) a2 = fmaf(f[j], w0[j], a2);
             if (saving) store_h32(hbuf, row, c0, f);
-            if (p.masks && rd.mask_off != kNone)
+            if (p.masks && rd.mask_off != kNone && tile_ok)
               p.masks[tile * p.mask_tile_words + rd.mask_off + (c0 >> 5) * 128 + row] = word;
           }
           if (valid) {
@@ -677,7 +759,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           }
         } else if (rd.epi == MCF_EPI_B_DPE) {
           // d_xyz += J_PE(x)^T dPE, with sin/cos taken from the saved first-layer operand image
-          const uint8_t* x0img = reinterpret_cast<const uint8_t*>(p.fwd_save) + tile * p.fwd_save_tile_bytes + p.fwd_x0_off;
+          const uint8_t* x0img = reinterpret_cast<const uint8_t*>(p.fwd_save) + tile_r * p.fwd_save_tile_bytes + p.fwd_x0_off;
           float pe[64];
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) {
@@ -725,7 +807,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             store_pending = true;
           }
         }
-        if (r + 1 < p.n_rounds) mbar_arrive(&tab.act_ready[s]);
+        if (r + 1 < p.n_rounds) arrive_act_ready();
         MCF_TACC(3, te);
       }
     }
@@ -739,8 +821,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
+  if (C == 2) cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading its operands
   if (timing && threadIdx.x == 0) p.timing[blockIdx.x * 16 + 12] = (unsigned long long)(clock64() - t_kernel0);
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) {
+    if (C == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -908,20 +993,40 @@ int mcf_chain_launch(const mcf_chain_params_t* pp, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
   }
   long long n_tiles = (p.n_rows + MCF_TILE_ROWS - 1) / MCF_TILE_ROWS;
-  long long n_pairs = (n_tiles + 1) / 2;
-  int cap = p.max_ctas > 0 ? p.max_ctas : n_sm;
-  int grid = (int)(n_pairs < cap ? n_pairs : cap);
+  const int ctas = (p.cta_pair != 0 && p.width == 256) ? 2 : 1;
+  long long n_units = (n_tiles + 2 * ctas - 1) / (2 * ctas);
+  int cap = (p.max_ctas > 0 ? p.max_ctas : n_sm) / ctas;
+  if (cap < 1) cap = 1;
+  int grid = (int)(n_units < cap ? n_units : cap) * ctas;
   cudaError_t e;
-  if (p.width == 256) {
+  if (p.width == 256 && ctas == 2) {
     const int smem = (int)mcf::Smem<256>::total;
-    e = cudaFuncSetAttribute(mcf::k_chain<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(mcf::k_chain<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    mcf::k_chain<256><<<grid, mcf::kThreads, smem, stream>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(mcf::kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, mcf::k_chain<256, 2>, p);
+    if (e != cudaSuccess) return (int)e;
+  } else if (p.width == 256) {
+    const int smem = (int)mcf::Smem<256>::total;
+    e = cudaFuncSetAttribute(mcf::k_chain<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    mcf::k_chain<256, 1><<<grid, mcf::kThreads, smem, stream>>>(p);
   } else if (p.width == 128) {
     const int smem = (int)mcf::Smem<128>::total;
-    e = cudaFuncSetAttribute(mcf::k_chain<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(mcf::k_chain<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    mcf::k_chain<128><<<grid, mcf::kThreads, smem, stream>>>(p);
+    mcf::k_chain<128, 1><<<grid, mcf::kThreads, smem, stream>>>(p);
   } else {
     return MCF_ERR_UNSUPPORTED;
   }

@@ -17,6 +17,10 @@ namespace mcf {
 
 constexpr int kDwThreads = 256;
 constexpr int kDwStages = 4;
+// bulk-copy issuing threads (lane 0 of warps 0, 2, 3): one issue occupies its thread for ~330 clk (measured,
+// scripts/dbg/mma_rate.cu), so a single producer feeding 6 x 8 KB per stage tops out near 22 B/clk/SM -- below the
+// ~23 B/clk/SM share of HBM bandwidth this kernel is supposed to reach
+constexpr int kDwProducers = 3;
 constexpr uint32_t kBlkD = MCF_BLOCK_BYTES;
 constexpr uint32_t kHalf = kBlkD / 2;                    // 64 rows of one 64-column block
 // one stage = 64 rows: P i-block (2 blocks) + Q (<= 4 blocks), 8 KB each -> 48 KB; 4 stages keep ~150 KB of
@@ -106,8 +110,9 @@ __device__ __forceinline__ void dw_body(const mcf_dw_params_t& p, int nib, int c
   long long my_tiles = 0;
   for (long long t = split; t < p.n_tiles; t += nsplit) ++my_tiles;
 
-  if (warp == 0) {
-    if (lane == 0) {
+  if (warp == 0 || warp == 2 || warp == 3) {
+    const uint32_t me = warp == 0 ? 0u : (uint32_t)warp - 1u;
+    if (lane == 0 && me < (uint32_t)kDwProducers) {
       uint32_t stage = 0, phase = 0;
       const uint8_t* pb = reinterpret_cast<const uint8_t*>(p.p_base);
       const uint8_t* qb = reinterpret_cast<const uint8_t*>(p.q_base);
@@ -116,12 +121,14 @@ __device__ __forceinline__ void dw_body(const mcf_dw_params_t& p, int nib, int c
         const uint8_t* qsrc = qb + t * p.q_tile_bytes + p.q_off;
         for (uint32_t half = 0; half < 2; ++half) {
           mbar_wait(&ctl.empty[stage], phase ^ 1u, 0x500u | stage);
-          mbar_arrive_expect_tx(&ctl.full[stage], (2 + q_blocks) * kHalf);
+          // producer 0 posts the stage's byte count; the others' complete_tx may land first (the phase cannot
+          // complete before producer 0's arrival)
+          if (me == 0) mbar_arrive_expect_tx(&ctl.full[stage], (2 + q_blocks) * kHalf);
           uint8_t* dst = smem + stage * kStageBytes;
-          for (uint32_t b = 0; b < 2; ++b)
-            bulk_g2s(dst + b * kHalf, psrc + b * kBlkD + half * kHalf, kHalf, &ctl.full[stage]);
-          for (uint32_t b = 0; b < q_blocks; ++b)
-            bulk_g2s(dst + (2 + b) * kHalf, qsrc + b * kBlkD + half * kHalf, kHalf, &ctl.full[stage]);
+          for (uint32_t b = me; b < 2 + q_blocks; b += kDwProducers) {
+            const uint8_t* src = b < 2 ? psrc + b * kBlkD : qsrc + (b - 2) * kBlkD;
+            bulk_g2s(dst + b * kHalf, src + half * kHalf, kHalf, &ctl.full[stage]);
+          }
           if (++stage == kDwStages) { stage = 0; phase ^= 1u; }
         }
       }

@@ -276,9 +276,9 @@ def flow_residual(x_obs, x_rec, alphas, fused_mean: bool = False):
 # fused MLP chains
 # ------------------------------------------------------------------------------------------------
 import os as _os
-# tiles in flight per CTA for the width-256 chain: 2 = ping-pong with a 4-stage weight ring, 1 = single tile with an
-# 8-stage ring (see mcf_chain_params_t.n_slots)
-NERF_SLOTS = int(_os.environ.get("MCF_NERF_SLOTS", "2"))
+# MCF_CTA_PAIR=1 runs the width-256 chains on CTA pairs (tcgen05 cta_group::2, see mcf_chain_params_t.cta_pair).
+# Parity-tested, but measured 3-6 % slower than one CTA per tile pair in round 1, hence off.
+CTA_PAIR = int(_os.environ.get("MCF_CTA_PAIR", "0"))
 
 
 class PackedPlan:
@@ -320,7 +320,7 @@ def chain_params(pp: PackedPlan, n_rows: int, rows_per_ray: int, n_rays: int) ->
     cp.fwd_x0_off = cp.fwd_he_off = L.NONE
     cp.extra_save_off = cp.dhead_save_off = L.NONE
     cp.out_stride, cp.sigma_col = 4, 3
-    cp.n_slots = NERF_SLOTS if pp.plan.width == 256 else 2
+    cp.cta_pair = CTA_PAIR if pp.plan.width == 256 else 0
     return cp
 
 

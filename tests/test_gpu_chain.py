@@ -132,6 +132,41 @@ def test_nerf_fused_pe_many_tiles(dev):
     assert e <= 1e-2 * sc
 
 
+@pytest.mark.parametrize("rows", [(37, 24), (64, 128), (3, 50)])
+def test_nerf_cta_pair_matches_single(dev, rows, monkeypatch):
+    """Width-256 chain on CTA pairs (tcgen05 cta_group::2, M=256 over two SMs) vs one CTA per tile pair: the same
+    accumulation order per output element, so forward, sigma-only and d_xyz are bit-identical; padding tiles of the
+    last pair (tile counts 7, 64, 2) must not be stored."""
+    import moco_flow_b200 as mf
+    from moco_flow_b200 import ops
+    R, S = rows
+    gen = torch.Generator().manual_seed(31)
+    xyz = (torch.rand(R * S, 3, generator=gen) - 0.5) * 2.0
+    ind = torch.rand(R, 1, generator=gen) * 2 - 1
+    up = torch.randn(R * S, 4, generator=gen).to(dev)
+    m = mf.NeRF(8, 256, 63, [4], "ind", 5)
+    m.load_state_dict(orc.make_nerf_params(orc.C2F_NERF, 5, dense=True))
+    m = m.to(dev)
+    pe, pe_i = mf.Embedding(3, 10), mf.Embedding(1, 2)
+    res = {}
+    for pair in (0, 1):
+        monkeypatch.setattr(ops, "CTA_PAIR", pair)
+        with torch.no_grad():
+            out = m.evaluate(xyz=xyz.to(dev), pe=pe, ray_feat=pe_i(ind.to(dev)), rows_per_ray=S)
+            sig = m.evaluate(xyz=xyz.to(dev), pe=pe, ray_feat=None, rows_per_ray=S, sigma_only=True)
+        xd = xyz.to(dev).requires_grad_(True)
+        for q in m.parameters():
+            q.grad = None
+        (m.evaluate(xyz=xd, pe=pe, ray_feat=pe_i(ind.to(dev)), rows_per_ray=S) * up).sum().backward()
+        torch.cuda.synchronize()
+        _no_device_error()
+        res[pair] = (out, sig, xd.grad.clone(), [q.grad.clone() for q in m.parameters()])
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert torch.equal(res[0][2], res[1][2])
+    for a, b in zip(res[0][3], res[1][3]):   # weight gradients: fp32 atomics, order differs run to run
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5 * float(a.abs().max()) + 1e-12)
+
+
 def _build_cuda_models(dev, nerfs, nofs, nerf_pes, nof_pes):
     import moco_flow_b200 as mf
     from tests.helpers import pe_module
