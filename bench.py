@@ -128,6 +128,7 @@ def run_ours(args):
     import moco_flow_b200 as mf
     from moco_flow_b200 import _lib as L
     from moco_flow_b200 import dp
+    from moco_flow_b200.optim import FusedAdam
     from moco_flow_b200.build import build
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -154,8 +155,9 @@ def run_ours(args):
     rays_h, bg_h, tgt_h = synth_batch(R, seed=1 + rank)
     rays_h, bg_h, tgt_h = rays_h.pin_memory(), bg_h.pin_memory(), tgt_h.pin_memory()
     rays_d, bg_d, tgt_d = rays_h.to(dev), bg_h.to(dev), tgt_h.to(dev)
-    flat = dp.FlatGradients(nerfs + nofs, fused_accumulate=True) if train else None
-    opt = torch.optim.Adam(flat.params, lr=5e-4, eps=1e-8, fused=True, capturable=True) if train else None
+    flat = dp.FlatGradients(nerfs + nofs, fused_accumulate=True, flatten_params=True) if train else None
+    # the reference's optimizer (trainer/base.py:122-133: Adam, eps 1e-8) as one fused launch over the flat buffers
+    opt = FusedAdam(flat.params, lr=5e-4, eps=1e-8) if train else None
     loss_fn = mf.MSELoss()
 
     def step(rays, bg, tgt):
@@ -168,8 +170,7 @@ def run_ours(args):
             loss = loss + 0.2 * (res["nof_local_disp_coarse"].mean() + res["nof_local_disp_fine"].mean())
             loss = loss + 0.2 * (res["nof_global_disp_coarse"].mean() + res["nof_global_disp_fine"].mean())
             loss.backward()
-            flat.allreduce_mean()
-            opt.step()
+            opt.step(grad_scale=flat.allreduce_sum())   # the 1/world of the gradient mean is folded into the update
             return loss.detach()
         with torch.no_grad():
             res = mf.render_rays(rays, bg, nerf_embs, nerfs, nof_embeddings=nof_embs, nof_models=nofs,

@@ -260,6 +260,16 @@ int mcf_unpack_accumulate(const mcf_unpack_t* table_dev, int n_entries, const fl
 /* out[c] += sum_m src[m*stride + c], c < ncols (<= 16): bias gradients of the heads */
 int mcf_colsum(const float* src, long long n_rows, int stride, int ncols, float* out, cudaStream_t stream);
 
+/* One Adam step over n contiguous fp32 elements (parameters, gradients and both moments are flat device arrays):
+ * torch.optim.Adam(lr, betas, eps, weight_decay) as built by trainer/base.py:122-133 and stepped at
+ * trainer/trainer_moco_flow.py:406-420.  g = grads*grad_scale (+ weight_decay*p);
+ * m += (1-b1)(g-m); v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps), t = *step_dev + 1.
+ * lr_dev / step_dev are device scalars (a captured CUDA graph keeps working while a scheduler changes the rate);
+ * advance_step != 0 increments *step_dev after the update (pass it on the last segment of an optimizer). */
+int mcf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                  const float* lr_dev, long long* step_dev, double beta1, double beta2, float eps, float weight_decay,
+                  float grad_scale, int advance_step, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

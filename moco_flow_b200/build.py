@@ -25,6 +25,7 @@ UNITS = [
     ("render_ops.cu", ["-fmad=false"]),
     ("chain.cu", []),
     ("gemm_dw.cu", []),
+    ("optim.cu", []),
 ]
 HEADERS = [os.path.join(CSRC, "ptx.cuh"), os.path.join(ROOT, "include", "moco_flow_b200.h")]
 

@@ -17,10 +17,9 @@ namespace mcf {
 
 constexpr int kDwThreads = 256;
 constexpr int kDwStages = 4;
-// bulk-copy issuing threads (lane 0 of warps 0, 2, 3): one issue occupies its thread for ~330 clk (measured,
-// scripts/dbg/mma_rate.cu), so a single producer feeding 6 x 8 KB per stage tops out near 22 B/clk/SM -- below the
-// ~23 B/clk/SM share of HBM bandwidth this kernel is supposed to reach
-constexpr int kDwProducers = 3;
+// bulk-copy issuing threads (lane 0 of warps 0, 2, 3).  Three were measured against one: no difference, the kernel
+// is not issue-bound.
+constexpr int kDwProducers = 1;
 constexpr uint32_t kBlkD = MCF_BLOCK_BYTES;
 constexpr uint32_t kHalf = kBlkD / 2;                    // 64 rows of one 64-column block
 // one stage = 64 rows: P i-block (2 blocks) + Q (<= 4 blocks), 8 KB each -> 48 KB; 4 stages keep ~150 KB of

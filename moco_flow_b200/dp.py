@@ -30,10 +30,15 @@ def shard_rays(rays: torch.Tensor, rank: int, world: int) -> torch.Tensor:
 class FlatGradients:
     """Flat gradient buffer shared by a list of modules; ``p.grad`` are views, so autograd accumulates in place."""
 
-    def __init__(self, modules: Iterable[torch.nn.Module], fused_accumulate: bool = False):
+    def __init__(self, modules: Iterable[torch.nn.Module], fused_accumulate: bool = False,
+                 flatten_params: bool = False):
         """``fused_accumulate``: let the fused MLP backward add its weight gradients straight into these ``.grad``
         views (moco_flow_b200.backward_mlp.ACCUMULATE_INTO_GRAD) instead of going through autograd's per-parameter
-        accumulation kernels.  Process-wide switch; use only with ``loss.backward()``."""
+        accumulation kernels.  Process-wide switch; use only with ``loss.backward()``.
+
+        ``flatten_params``: also move the parameters themselves into one flat buffer (``p.data`` become views, in the
+        same order as the gradients), so that ``optim.FusedAdam`` updates all of them with one launch and
+        ``broadcast_parameters`` is a single collective.  ``state_dict`` names and shapes are unchanged."""
         if fused_accumulate:
             from . import backward_mlp
             backward_mlp.ACCUMULATE_INTO_GRAD = True
@@ -49,13 +54,31 @@ class FlatGradients:
         dev, dt = self.params[0].device, self.params[0].dtype
         self.numel = sum(p.numel() for p in self.params)
         self.buffer = torch.zeros(self.numel, device=dev, dtype=dt)
+        self.param_buffer = None
+        if flatten_params:
+            self.param_buffer = torch.empty(self.numel, device=dev, dtype=dt)
         off = 0
         for p in self.params:
+            if flatten_params:
+                view = self.param_buffer[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
             p.grad = self.buffer[off:off + p.numel()].view_as(p)
             off += p.numel()
 
     def zero(self) -> None:
         self.buffer.zero_()
+
+    def allreduce_sum(self, group=None) -> float:
+        """Sum over ranks; returns the factor (1/world) the caller still has to apply -- ``FusedAdam.step(grad_scale=)``
+        folds it into the update instead of spending a pass over the buffer."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1.0
+        world = dist.get_world_size(group)
+        if world == 1:
+            return 1.0
+        dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group)
+        return 1.0 / world
 
     def allreduce_mean(self, group=None) -> None:
         """Sum over ranks then divide by the world size (no-op without an initialised process group)."""

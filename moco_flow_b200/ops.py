@@ -281,6 +281,16 @@ import os as _os
 CTA_PAIR = int(_os.environ.get("MCF_CTA_PAIR", "0"))
 
 
+# bumped by writers that update parameters behind autograd's back (optim.FusedAdam writes through raw pointers, which
+# does not advance the tensors' version counters): packed bf16 weight images are rebuilt when it changes
+PARAM_EPOCH = 0
+
+
+def bump_param_epoch() -> None:
+    global PARAM_EPOCH
+    PARAM_EPOCH += 1
+
+
 class PackedPlan:
     """A plan's device-side tables plus the packed weight buffers of one module."""
 
@@ -297,7 +307,7 @@ class PackedPlan:
 
     def repack(self, params: Dict[str, torch.Tensor]) -> None:
         tensors = [params[n] for n in self.plan.tensor_names]
-        versions = tuple((t.data_ptr(), t._version) for t in tensors)
+        versions = (PARAM_EPOCH,) + tuple((t.data_ptr(), t._version) for t in tensors)
         if versions == self.versions:
             return
         for t in tensors:

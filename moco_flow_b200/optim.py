@@ -1,0 +1,122 @@
+"""Fused Adam for the training step that follows the ray-rendering backward.
+
+``FusedAdam`` is a ``torch.optim.Optimizer`` with the constructor and ``param_groups`` of ``torch.optim.Adam``
+as the reference builds it (trainer/base.py:122-133: ``Adam(parameters, lr=..., eps=1e-8, weight_decay=...)``), so the
+reference's ``MultiStepLR`` / ``ExponentialLR`` / ... schedulers (trainer/base.py:141-160) and its two-optimizer
+arrangement over overlapping parameter sets (trainer/trainer_moco_flow.py:121-139, stepped one after the other at
+trainer/base.py:188-197) work unchanged.  Parameters whose storage and ``.grad`` storage are adjacent -- what
+``dp.FlatGradients(..., flatten_params=True)`` produces -- are merged into segments and each segment is one
+``mcf_adam_step`` launch (csrc/optim.cu); the step count and learning rate are device scalars, so a captured CUDA
+graph of the step stays valid while a scheduler keeps changing ``group['lr']`` (call ``sync_lr()`` outside the graph).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+def merge_segments(items: List[Tuple[int, int, int]]) -> List[Tuple[int, int, int, List[int]]]:
+    """``items``: (param_ptr, grad_ptr, numel) per parameter.  Returns maximal runs that are contiguous in both the
+    parameter and the gradient address space as (param_ptr, grad_ptr, numel, member indices), in address order."""
+    order = sorted(range(len(items)), key=lambda i: items[i][0])
+    segs: List[Tuple[int, int, int, List[int]]] = []
+    for i in order:
+        p, g, n = items[i]
+        if n == 0:
+            continue
+        if segs:
+            sp, sg, sn, members = segs[-1]
+            if sp + 4 * sn == p and sg + 4 * sn == g:
+                segs[-1] = (sp, sg, sn + n, members + [i])
+                continue
+        segs.append((p, g, n, [i]))
+    return segs
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0):
+        if lr < 0.0 or eps < 0.0 or weight_decay < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0):
+            raise ValueError("invalid Adam hyper-parameter")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._plans: Dict[int, dict] = {}
+
+    # ---- segment plan of one param group (rebuilt when storage pointers change) ----
+    def _plan(self, gi: int, group: dict) -> dict:
+        ps = [p for p in group["params"] if p.grad is not None]
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), p.numel()) for p in ps)
+        plan = self._plans.get(gi)
+        if plan is not None and plan["key"] == key:
+            return plan
+        for p in ps:
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()
+                    and p.grad.dtype == torch.float32):
+                raise RuntimeError("FusedAdam needs contiguous CUDA float32 parameters and gradients (no CPU fallback)")
+        dev = ps[0].device if ps else torch.device("cuda")
+        old = plan
+        segs = merge_segments(list(key))
+        total = sum(s[2] for s in segs)
+        m = torch.zeros(total, device=dev)
+        v = torch.zeros(total, device=dev)
+        step = old["step"] if old is not None else torch.zeros(1, dtype=torch.int64, device=dev)
+        lr_dev = old["lr_dev"] if old is not None else torch.full((1,), float(group["lr"]), device=dev)
+        off = 0
+        seg_off = []
+        for sp, sg, sn, members in segs:
+            o = off
+            for i in members:
+                p = ps[i]
+                st = self.state[p]
+                for name, buf in (("exp_avg", m), ("exp_avg_sq", v)):
+                    view = buf[o:o + p.numel()].view_as(p)
+                    if name in st:            # keep moments across a re-plan / load_state_dict
+                        view.copy_(st[name])
+                    st[name] = view
+                st["step"] = step
+                o += p.numel()
+            seg_off.append(off)
+            off += sn
+        plan = dict(key=key, segs=segs, seg_off=seg_off, m=m, v=v, step=step, lr_dev=lr_dev, lr_host=None)
+        self._plans[gi] = plan
+        return plan
+
+    def sync_lr(self) -> None:
+        """Copies every group's ``lr`` to its device scalar (call after a scheduler step, outside graph capture)."""
+        for gi, group in enumerate(self.param_groups):
+            plan = self._plans.get(gi)
+            if plan is not None and plan["lr_host"] != float(group["lr"]):
+                plan["lr_dev"].fill_(float(group["lr"]))
+                plan["lr_host"] = float(group["lr"])
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        """One Adam update of every group.  ``grad_scale`` multiplies the gradients first (1/world after a summing
+        all-reduce)."""
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        for gi, group in enumerate(self.param_groups):
+            plan = self._plan(gi, group)
+            if not capturing and plan["lr_host"] != float(group["lr"]):
+                plan["lr_dev"].fill_(float(group["lr"]))
+                plan["lr_host"] = float(group["lr"])
+            b1, b2 = group["betas"]
+            n_seg = len(plan["segs"])
+            for k, ((sp, sg, sn, _), so) in enumerate(zip(plan["segs"], plan["seg_off"])):
+                L.check(L.lib().mcf_adam_step(
+                    C.c_void_p(sp), C.c_void_p(sg), C.c_void_p(plan["m"].data_ptr() + 4 * so),
+                    C.c_void_p(plan["v"].data_ptr() + 4 * so), C.c_longlong(sn), L.ptr(plan["lr_dev"]),
+                    L.ptr(plan["step"]), C.c_double(b1), C.c_double(b2), C.c_float(group["eps"]),
+                    C.c_float(group["weight_decay"]), C.c_float(grad_scale), C.c_int(1 if k == n_seg - 1 else 0),
+                    L.stream_ptr()), "mcf_adam_step")
+                if k == n_seg - 1:
+                    L.LAUNCHES += 1   # the step-counter tick kernel
+        ops.bump_param_epoch()   # raw-pointer writes: tell the modules to re-pack their bf16 weight images
+        return loss
