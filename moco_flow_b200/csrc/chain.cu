@@ -372,11 +372,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
               const uint32_t b_base = ring_addr + stage * kBlk;
               const uint32_t idesc = make_idesc(fuse ? 2u * ch.n : (uint32_t)ch.n, false, false, 128u * C);
               const uint32_t d_tmem = tmem_base + s * kSlotCols + ch.acc_col;
-              for (uint32_t k = 0; k < ch.ksteps; ++k) {
-                const uint64_t ad = make_sdesc(a_base + k * 32u, 0u, 1024u);
-                const uint64_t bd = make_sdesc(b_base + k * 32u, 0u, 1024u);
-                if (C == 2) umma_bf16_pair(d_tmem, ad, bd, idesc, (k > 0u || !(ch.flags & 1u)) ? 1u : 0u);
-                else umma_bf16(d_tmem, ad, bd, idesc, (k > 0u || !(ch.flags & 1u)) ? 1u : 0u);
+              // one thread feeds the tensor core: keep the per-instruction work to two 64-bit adds (a K step of 16
+              // bf16 = 32 B moves the 16-byte-unit start-address field of both descriptors by 2)
+              uint64_t ad = make_sdesc(a_base, 0u, 1024u), bd = make_sdesc(b_base, 0u, 1024u);
+              uint32_t acc = (ch.flags & 1u) ? 0u : 1u;
+              if (ch.ksteps == 4) {
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) {
+                  if (C == 2) umma_bf16_pair(d_tmem, ad + 2u * k, bd + 2u * k, idesc, k ? 1u : acc);
+                  else umma_bf16(d_tmem, ad + 2u * k, bd + 2u * k, idesc, k ? 1u : acc);
+                }
+              } else {
+                for (uint32_t k = 0; k < ch.ksteps; ++k) {
+                  if (C == 2) umma_bf16_pair(d_tmem, ad, bd, idesc, acc);
+                  else umma_bf16(d_tmem, ad, bd, idesc, acc);
+                  ad += 2u; bd += 2u; acc = 1u;
+                }
               }
               if (C == 2) {
                 umma_commit_pair(&tab.w_empty[stage], 3);   // frees the stage in both CTAs

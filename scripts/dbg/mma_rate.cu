@@ -104,6 +104,38 @@ __global__ void __launch_bounds__(256, 1) k_copy_mt(const uint8_t* src, int tota
   }
 }
 
+// n_mma MMAs (N=256) with a tcgen05.commit to a rotating mbarrier after every `group` of them: does a commit
+// put a bubble into the tensor pipe?
+__global__ void __launch_bounds__(128, 1) k_commit(int n_mma, int group, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tbase;
+  __shared__ uint64_t bar[8], done;
+  int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1); mbar_init(&done, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(&tbase, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  if (threadIdx.x == 32) {
+    const uint32_t a = smem_u32(smem), b = smem_u32(smem) + 16384;
+    const uint32_t idesc = make_idesc(256u);
+    long long t0 = clock64();
+    int nb = 0;
+    for (int i = 0; i < n_mma; ++i) {
+      const uint32_t k = i & 3;
+      umma_bf16(tbase + ((i >> 2) & 1) * 256, make_sdesc(a + k * 32, 0, 1024), make_sdesc(b + k * 32, 0, 1024), idesc,
+                (i > 7) ? 1u : 0u);
+      if ((i + 1) % group == 0) { umma_commit(&bar[nb & 7]); ++nb; }
+    }
+    umma_commit(&done);
+    mbar_wait(&done, 0);
+    long long t2 = clock64();
+    out[blockIdx.x * 2 + 1] = (unsigned long long)(t2 - t0);
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
 int main() {
   unsigned long long* out;
   cudaMalloc(&out, 148 * 16);
@@ -120,6 +152,13 @@ int main() {
                h[0], (double)h[0] / n, h[1], (double)h[1] / n, cudaGetErrorString(cudaGetLastError()));
       }
     }
+  }
+  cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  for (int group : {1, 2, 4, 8, 16, 1024}) {
+    k_commit<<<148, 128, 64 * 1024>>>(1024, group, out);
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("commit every %4d MMAs (N=256): %.1f clk/mma (ideal 128)  %s\n", group, (double)h[1] / 1024, cudaGetErrorString(cudaGetLastError()));
   }
   uint8_t* src;
   const int total = 1216 * 1024;
