@@ -270,6 +270,21 @@ int mcf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   const float* lr_dev, long long* step_dev, double beta1, double beta2, float eps, float weight_decay,
                   float grad_scale, int advance_step, cudaStream_t stream);
 
+/* ---- ray generation / canvas scatter ------------------------------------------- */
+/* utils/camera.py:29-82,134-148: rows [o(3) d(3) near far img_ind] for n_rays pixels of an H x W pinhole camera.
+ * Pixel p = j*W + i has camera direction ((i-cx)/focal, -(j-cy)/focal, -1) (no half-pixel offset, one focal for both
+ * axes as in the reference), rotated by c2w (host pointer to a row-major [3][4]; NULL = camera frame, origin 0) and
+ * normalised.  pixel_index (device, int64) selects pixels -- the valid-ray mask gather of
+ * trainer/trainer_moco_flow.py:229-232 -- or NULL for pixels 0..n_rays-1. */
+int mcf_make_rays(int H, int W, float focal, float cx, float cy, const float* c2w_host, float near, float far,
+                  float img_ind, const long long* pixel_index, long long n_rays, float* rays, int ray_stride,
+                  cudaStream_t stream);
+/* trainer/trainer_moco_flow.py:247-262: img_out[n_pixels][3] = background, depth_out = 10; the n_rays rendered
+ * pixels (pixel_index, or 0..n_rays-1) get depth 8, and where opacity > 0 the rendered rgb / depth. */
+int mcf_canvas_scatter(const float* background, long long n_pixels, const long long* pixel_index, long long n_rays,
+                       const float* rgb, const float* depth, const float* opacity, float* img_out, float* depth_out,
+                       cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,7 @@ UNITS = [
     ("chain.cu", []),
     ("gemm_dw.cu", []),
     ("optim.cu", []),
+    ("camera.cu", ["-fmad=false"]),
 ]
 HEADERS = [os.path.join(CSRC, "ptx.cuh"), os.path.join(ROOT, "include", "moco_flow_b200.h")]
 
