@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             for (int c = cb; c < ce; ++c) {
               if (tab.chunks[c].flags & 2u) ++c;
               mbar_wait(&tab.w_full[stage], phase, 0x500u | stage);
-              mbar_arrive_cluster(peer_bar[stage]);
+              mbar_arrive_cluster_relaxed(peer_bar[stage]);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
           }

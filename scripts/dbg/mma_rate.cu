@@ -136,6 +136,38 @@ __global__ void __launch_bounds__(128, 1) k_commit(int n_mma, int group, unsigne
   if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
+// raw cta_group::2 rate: the leader of a CTA pair issues n M=256 N=256 K=16 MMAs on resident operands
+__global__ void __launch_bounds__(128, 1) k_mma_pair(int n_mma, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tbase;
+  __shared__ uint64_t bar;
+  int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc_pair(&tbase, 512); tmem_relinquish_pair(); }
+  fence_proxy_async_smem();
+  tc_fence_before(); __syncthreads(); cluster_sync_all(); tc_fence_after();
+  if (threadIdx.x == 32 && rank == 0) {
+    const uint32_t a = smem_u32(smem), b = smem_u32(smem) + 16384;
+    const uint32_t idesc = make_idesc(256u, false, false, 256u);
+    const uint64_t ad = make_sdesc(a, 0, 1024), bd = make_sdesc(b, 0, 1024);
+    long long t0 = clock64();
+    for (int i = 0; i < n_mma; ++i) {
+      const uint32_t k = i & 3;
+      umma_bf16_pair(tbase + ((i >> 2) & 1) * 256, ad + 2 * k, bd + 2 * k, idesc, (i > 7) ? 1u : 0u);
+    }
+    umma_commit_pair(&bar, 1);
+    long long t1 = clock64();
+    mbar_wait(&bar, 0);
+    long long t2 = clock64();
+    out[blockIdx.x * 2 + 0] = (unsigned long long)(t1 - t0);
+    out[blockIdx.x * 2 + 1] = (unsigned long long)(t2 - t0);
+  }
+  tc_fence_before(); __syncthreads(); cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair(tbase, 512);
+}
+
 int main() {
   unsigned long long* out;
   cudaMalloc(&out, 148 * 16);
@@ -152,6 +184,20 @@ int main() {
                h[0], (double)h[0] / n, h[1], (double)h[1] / n, cudaGetErrorString(cudaGetLastError()));
       }
     }
+  }
+  cudaFuncSetAttribute(k_mma_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  for (int n : {16, 256, 4096}) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(148); lc.blockDim = dim3(128); lc.dynamicSmemBytes = 64 * 1024; lc.stream = 0;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    cudaLaunchKernelEx(&lc, k_mma_pair, n, out);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("pair mma M=256 N=256 n=%4d: issue %.1f clk/mma, complete %.1f clk/mma (ideal 128)  %s\n", n, (double)h[0] / n,
+           (double)h[1] / n, cudaGetErrorString(e));
   }
   cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   for (int group : {1, 2, 4, 8, 16, 1024}) {

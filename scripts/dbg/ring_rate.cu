@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128, 1) k_ring_pair(const uint8_t* src, int to
         uint32_t stage = 0, phase = 0; int turn = 0;
         for (int c = 0; c < n_st; ++c) {
           if (turn == me) {
-            mbar_wait_cluster(&w_empty[stage], phase ^ 1u);
+            if (cfg.timing == 2) mbar_wait(&w_empty[stage], phase ^ 1u); else mbar_wait_cluster(&w_empty[stage], phase ^ 1u);
             mbar_arrive_expect_tx(&w_full[stage], 16384);
             bulk_g2s(ring + stage * 16384, src + ((size_t)(2 * c + rank) * 16384) % total_bytes, 16384, &w_full[stage]);
           }
@@ -113,12 +113,28 @@ __global__ void __launch_bounds__(128, 1) k_ring_pair(const uint8_t* src, int to
         }
       }
     }
-  } else if (lane == 0 && rank != 0) {
-    uint32_t stage = 0, phase = 0;
-    for (int c = 0; c < n_st; ++c) {
-      mbar_wait(&w_full[stage], phase);
-      mbar_arrive_cluster(map_to_cta(smem_u32(&w_peer[stage]), 0));
-      if (++stage == S) { stage = 0; phase ^= 1u; }
+  } else if (rank != 0) {
+    // relay modes (cfg.fence): 0 = one thread, release.cluster arrive; 1 = one thread, relaxed arrive;
+    // 2 = one lane per stage, release arrive
+    if (cfg.fence == 2) {
+      if (lane < S) {
+        const uint32_t remote = map_to_cta(smem_u32(&w_peer[lane]), 0);
+        uint32_t phase = 0;
+        for (int c = lane; c < n_st; c += S) {
+          mbar_wait(&w_full[lane], phase);
+          mbar_arrive_cluster(remote);
+          phase ^= 1u;
+        }
+      }
+    } else if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int c = 0; c < n_st; ++c) {
+        mbar_wait(&w_full[stage], phase);
+        const uint32_t remote = map_to_cta(smem_u32(&w_peer[stage]), 0);
+        if (cfg.fence == 1) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+        else mbar_arrive_cluster(remote);
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
     }
   } else if (lane == 0) {
     uint32_t stage = 0, phase = 0;
@@ -128,7 +144,7 @@ __global__ void __launch_bounds__(128, 1) k_ring_pair(const uint8_t* src, int to
     const uint32_t idesc = make_idesc(256u, false, false, 256u);
     for (int c = 0; c < n_st; ++c) {
       mbar_wait(&w_full[stage], phase);
-      mbar_wait_cluster(&w_peer[stage], phase);
+      if (cfg.timing == 2) mbar_wait(&w_peer[stage], phase); else mbar_wait_cluster(&w_peer[stage], phase);
       tc_fence_after();
       if (cfg.timing) { long long n = clock64(); t_wait += n - t; t = n; }
       const uint32_t a_base = a_addr + (c & 3) * 16384, b_base = r_addr + stage * 16384;
@@ -171,8 +187,8 @@ int main() {
            fence, prod, timing, (double)h[0] / chunks, (double)h[1] / chunks, (double)h[2] / chunks, cudaGetErrorString(e));
   }
   cudaFuncSetAttribute(k_ring_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  for (int stages : {4, 8}) for (int prod : {1, 3}) for (int timing : {1, 0}) {
-    Cfg cfg{stages, 1, 1, prod, chunks, timing};
+  for (int stages : {4, 8}) for (int prod : {1}) for (int relay : {0, 1, 2}) for (int timing : {1, 2}) {
+    Cfg cfg{stages, 1, relay, prod, chunks, timing};
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(148); lc.blockDim = dim3(128); lc.dynamicSmemBytes = 200 * 1024; lc.stream = 0;
     cudaLaunchAttribute at[1];
@@ -183,8 +199,8 @@ int main() {
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
     // same FLOPs per SM as the single-CTA runs: `chunks` K=64 x N=128 blocks of tensor work per CTA -> ideal 256 clk/chunk
-    printf("PAIR stages=%d producers=%d timing=%d: %.1f clk/chunk-equivalent (ideal 256), wait %.1f issue %.1f  %s\n", stages,
-           prod, timing, (double)h[0] / chunks, (double)h[1] / chunks, (double)h[2] / chunks, cudaGetErrorString(e));
+    printf("PAIR stages=%d producers=%d relay=%d waits=%s: %.1f clk/chunk-equivalent (ideal 256), wait %.1f issue %.1f  %s\n", stages,
+           prod, relay, timing == 2 ? "cta" : "cluster", (double)h[0] / chunks, (double)h[1] / chunks, (double)h[2] / chunks, cudaGetErrorString(e));
   }
   return 0;
 }
