@@ -212,12 +212,21 @@ class _NeRFFn(torch.autograd.Function):
 
 
 def nerf_autograd(model, xyz, pe, dense, ray_feat, rows_per_ray, sigma_only):
-    if sigma_only:
-        raise NotImplementedError("differentiating the sigma-only evaluation is not part of the render path")
     if dense is not None and dense.requires_grad:
         raise NotImplementedError("gradients w.r.t. pre-embedded inputs are not provided; pass xyz + Embedding")
     names = [n for n, _ in model.named_parameters()]
     params = [p for _, p in model.named_parameters()]
+    if sigma_only:
+        # Differentiable sigma-only evaluation (the auxiliary density loss on point batches,
+        # trainer/trainer_moco_flow.py:146-158,349-361): sigma does not depend on the extra feature, so this runs the
+        # full differentiable program with a zero feature row and returns its sigma column; the colour branch then
+        # receives exactly-zero gradients.
+        M = int(dense.shape[0] if dense is not None else xyz.shape[0])
+        E = model._extra_dim()
+        dev = (dense if dense is not None else xyz).device
+        zero_feat = torch.zeros(M // rows_per_ray, E, device=dev) if E > 0 else None
+        out = _NeRFFn.apply(model, pe, rows_per_ray, xyz, dense, zero_feat, names, *params)
+        return out[:, 3:4]
     return _NeRFFn.apply(model, pe, rows_per_ray, xyz, dense, ray_feat, names, *params)
 
 

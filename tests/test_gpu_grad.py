@@ -106,6 +106,45 @@ def test_nerf_fused_gradients(dev):
     compare_grads("nerf", got, list(zip(names + ["d_xyz"], gem)), 3e-2, list(zip(names + ["d_xyz"], g32)))
 
 
+def test_nerf_sigma_only_gradients(dev):
+    """Auxiliary density loss on a point batch (trainer/trainer_moco_flow.py:146-158,349-361): sigma-only evaluation,
+    alpha = 1 - exp(-delta * softplus(sigma)), gradients to the trunk + sigma head and to the points."""
+    import moco_flow_b200 as mf
+    gen = torch.Generator().manual_seed(33)
+    N = 700  # 6 tiles, last partial; one "ray" holding all points
+    xyz = (torch.rand(N, 3, generator=gen) - 0.5) * 1.2
+    up = torch.rand(N, 1, generator=gen)
+    p = orc.make_nerf_params(orc.C2F_NERF, 12, dense=True)
+    m = mf.NeRF(8, 256, 63, [4], "ind", 5)
+    m.load_state_dict(p)
+    m = m.to(dev)
+    pe = mf.Embedding(3, 10)
+    delta = 1.0 / 64
+    xd = xyz.to(dev).requires_grad_(True)
+    sig = m.evaluate(xyz=xd, pe=pe, rows_per_ray=N, sigma_only=True)
+    assert sig.shape == (N, 1)
+    ((1 - torch.exp(-delta * torch.nn.functional.softplus(sig))) * up.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    from moco_flow_b200 import _lib as L
+    assert L.device_error_flag() == 0
+    po = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    xo = xyz.clone().requires_grad_(True)
+    trunk = [n for n, _ in m.named_parameters() if n.startswith("xyz_encoding_") and "final" not in n or n.startswith("sigma")]
+
+    def run():
+        feats = torch.cat([orc.positional_encoding(xo, orc.PESpec(3, 10)), torch.zeros(N, 5)], 1)
+        s_ = orc.nerf_mlp(po, orc.C2F_NERF, feats)[:, 3:4]
+        return ((1 - torch.exp(-delta * torch.nn.functional.softplus(s_))) * up).sum()
+    g32, gem = oracle_grads(run, [po[n] for n in trunk] + [xo])
+    named = dict(m.named_parameters())
+    got = [(n, named[n].grad) for n in trunk] + [("d_xyz", xd.grad)]
+    compare_grads("nerf sigma-only", got, list(zip(trunk + ["d_xyz"], gem)), 3e-2, list(zip(trunk + ["d_xyz"], g32)))
+    # the colour branch is untouched by this loss
+    for n, q in m.named_parameters():
+        if n not in trunk:
+            assert q.grad is None or float(q.grad.abs().max()) == 0.0, n
+
+
 @pytest.mark.parametrize("use_quat", [True, False])
 def test_nof_fused_gradients(dev, use_quat):
     import moco_flow_b200 as mf
