@@ -62,6 +62,9 @@ static_assert(Smem<256>::total <= 232448 && Smem<128>::total <= 232448, "shared 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store_h8(uint8_t* hbuf, uint32_t row, uint32_t col0, uint4 v) {
   uint32_t block = col0 >> 6, c16 = (col0 & 63u) >> 3;
+#ifdef MCF_EXP_NOSTS   // timing experiment only (wrong results): drop the activation stores unless a value is "magic"
+  if (v.x != 0x7fc12345u) return;
+#endif
   *reinterpret_cast<uint4*>(hbuf + block * kBlk + sw128_off(row, c16)) = v;
 }
 
@@ -86,7 +89,11 @@ __device__ __forceinline__ void load32f(const float* __restrict__ p, float (&b)[
 #endif
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
+    // biases / head weights are re-read by every tile: ask L1 (only ~28 KB next to the 227 KB carve-out) to keep them
+    float4 t;
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                 : "l"(reinterpret_cast<const float4*>(p) + q));
     b[q * 4 + 0] = t.x;
     b[q * 4 + 1] = t.y;
     b[q * 4 + 2] = t.z;

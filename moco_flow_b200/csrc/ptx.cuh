@@ -229,6 +229,11 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_
 
 // TMEM -> registers, 32 lanes x 32-bit, N consecutive columns; thread t of the warp gets lane (base+t).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+#ifdef MCF_EXP_NOLDTM  // timing experiment only (wrong results): no TMEM read, values derived from the address
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = taddr * 2654435761u + i;
+  return;
+#endif
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
