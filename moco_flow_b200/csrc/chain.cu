@@ -110,9 +110,16 @@ __device__ __forceinline__ uint32_t bias_act_store32(uint8_t* hbuf, uint32_t row
   for (int j = 0; j < 16; ++j) add_f32x2(v[2 * j], v[2 * j + 1], b[2 * j], b[2 * j + 1]);
   uint32_t word = 0;
   if (kMask) {
+    // sign bits -> bit j of the word; four independent 8-deep funnel-shift chains instead of one 32-deep one
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
 #pragma unroll
-    for (int j = 31; j >= 0; --j) word = __funnelshift_l(v[j], word, 1);  // collects sign bits, bit j <- v[j]
-    word = ~word;
+    for (int j = 7; j >= 0; --j) {
+      w0 = __funnelshift_l(v[j], w0, 1);
+      w1 = __funnelshift_l(v[8 + j], w1, 1);
+      w2 = __funnelshift_l(v[16 + j], w2, 1);
+      w3 = __funnelshift_l(v[24 + j], w3, 1);
+    }
+    word = ~(w0 | (w1 << 8) | (w2 << 16) | (w3 << 24));
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -283,7 +290,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
   const long long unit0 = blockIdx.x / C, unit_step = gridDim.x / C;
   auto tile_of = [&](long long u, int s) -> long long { return (2 * u + s) * C + cta_rank; };
   auto wait_x = [&](uint64_t* bar, uint32_t parity, uint32_t tag) {
-    if (C == 2) mbar_wait_cluster(bar, parity, tag); else mbar_wait(bar, parity, tag);
+    // cta-scope acquire also for barriers signalled from the peer CTA (as CUTLASS' ClusterBarrier::wait does): what
+    // they guard is either async-proxy data (weights) or this SM's own shared memory / TMEM
+    mbar_wait(bar, parity, tag);
   };
 
   // register re-distribution between the warpgroups: the producer/MMA/allocator warpgroup needs few registers,
@@ -371,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
               // flag bit1: this chunk and the next one are the two 128-row halves of one [256 x 64] weight tile
               // sitting in consecutive (even, odd) ring stages -> one N=256 instruction per K step
               const bool fuse = (ch.flags & 2u) != 0u;
-              if (C == 2) mbar_wait_cluster(&tab.w_peer[stage], phase, 0x600u | stage);
+              if (C == 2) mbar_wait(&tab.w_peer[stage], phase, 0x600u | stage);
               else if (fuse) mbar_wait(&tab.w_full[stage + 1], phase, 0x300u | (stage + 1));
               tc_fence_after();
               MCF_TACC(1, tm);
@@ -436,8 +445,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     const uint32_t act_ready_leader = (C == 2) ? map_to_cta(smem_u32(&tab.act_ready[s]), 0u) : 0u;
     auto arrive_act_ready = [&]() {
       if (C == 2) {
+        // Every lane has already executed fence.proxy.async after its st.shared (the operand is read by this SM's own
+        // tensor core), so the remote arrival only carries control: a release at cluster scope here also drains the
+        // warp's global stores and was measured at ~1300 clk per round.
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(act_ready_leader);
+        if (lane == 0) mbar_arrive_cluster_relaxed(act_ready_leader);
       } else {
         mbar_arrive(&tab.act_ready[s]);
       }

@@ -276,9 +276,10 @@ def flow_residual(x_obs, x_rec, alphas, fused_mean: bool = False):
 # fused MLP chains
 # ------------------------------------------------------------------------------------------------
 import os as _os
-# MCF_CTA_PAIR=1 runs the width-256 chains on CTA pairs (tcgen05 cta_group::2, see mcf_chain_params_t.cta_pair).
-# Parity-tested, but measured 3-6 % slower than one CTA per tile pair in round 1, hence off.
-CTA_PAIR = int(_os.environ.get("MCF_CTA_PAIR", "0"))
+# Width-256 chains run on CTA pairs (tcgen05 cta_group::2, see mcf_chain_params_t.cta_pair): bit-identical to the
+# one-CTA-per-tile-pair path (tests/test_gpu_chain.py::test_nerf_cta_pair_matches_single), 8-9 % faster on the training
+# chains, equal on inference.  MCF_CTA_PAIR=0 selects the single-CTA path.
+CTA_PAIR = int(_os.environ.get("MCF_CTA_PAIR", "1"))
 
 
 # bumped by writers that update parameters behind autograd's back (optim.FusedAdam writes through raw pointers, which
