@@ -69,6 +69,16 @@ class FlatGradients:
     def zero(self) -> None:
         self.buffer.zero_()
 
+    def broadcast_parameters(self, src: int = 0, group=None) -> None:
+        """Rank ``src``'s weights to everyone: one collective when the parameters are flattened."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        if self.param_buffer is not None:
+            dist.broadcast(self.param_buffer, src=src, group=group)
+        else:
+            for p in self.params:
+                dist.broadcast(p.data, src=src, group=group)
+
     def allreduce_sum(self, group=None) -> float:
         """Sum over ranks; returns the factor (1/world) the caller still has to apply -- ``FusedAdam.step(grad_scale=)``
         folds it into the update instead of spending a pass over the buffer."""

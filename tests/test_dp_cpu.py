@@ -60,3 +60,37 @@ def test_two_rank_gradients_match_single_process(tmp_path):
     torch.nn.functional.mse_loss(net(blob["rays"]), blob["target"]).backward()
     ref = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
     assert torch.allclose(blob["grad"], ref, atol=1e-6)
+
+
+def _worker_flat(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(rank)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    # flattened parameters: one broadcast of the flat buffer makes every rank identical
+    flat = dp.FlatGradients([net], flatten_params=True)
+    flat.broadcast_parameters(src=0)
+    gen = torch.Generator().manual_seed(123)
+    rays = torch.randn(10, 6, generator=gen)
+    target = torch.randn(10, 3, generator=gen)
+    b, e = dp.shard_bounds(10, rank, world)
+    flat.zero()
+    torch.nn.functional.mse_loss(net(rays[b:e]), target[b:e]).backward()
+    scale = flat.allreduce_sum()       # sum only; the 1/world goes into the optimizer step
+    assert scale == 1.0 / world
+    if rank == 0:
+        torch.save(dict(grad=flat.buffer.clone() * scale, params=flat.param_buffer.clone(),
+                        state={k: v.clone() for k, v in net.state_dict().items()}, rays=rays, target=target), out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_flat_parameters_and_sum_allreduce(tmp_path):
+    out = str(tmp_path / "r0_flat.pt")
+    mp.spawn(_worker_flat, args=(2, _free_port(), out), nprocs=2, join=True)
+    blob = torch.load(out)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    net.load_state_dict(blob["state"])
+    assert torch.equal(torch.cat([p.detach().reshape(-1) for p in net.parameters()]), blob["params"])
+    torch.nn.functional.mse_loss(net(blob["rays"]), blob["target"]).backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    assert torch.allclose(blob["grad"], ref, atol=1e-6)
