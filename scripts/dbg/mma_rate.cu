@@ -137,12 +137,14 @@ __global__ void __launch_bounds__(128, 1) k_commit(int n_mma, int group, unsigne
 }
 
 // raw cta_group::2 rate: the leader of a CTA pair issues n M=256 N=256 K=16 MMAs on resident operands
-__global__ void __launch_bounds__(128, 1) k_mma_pair(int n_mma, unsigned long long* out) {
+__global__ void __launch_bounds__(128, 1) k_mma_pair(int n_mma, unsigned long long* out, int commit_every = 0, int mask = 3) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tbase;
   __shared__ uint64_t bar;
+  __shared__ uint64_t rot[8];
   int warp = threadIdx.x >> 5;
   const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) for (int i = 0; i < 8; ++i) mbar_init(&rot[i], 1);
   for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   if (warp == 0) { tmem_alloc_pair(&tbase, 512); tmem_relinquish_pair(); }
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(128, 1) k_mma_pair(int n_mma, unsigned long lo
     for (int i = 0; i < n_mma; ++i) {
       const uint32_t k = i & 3;
       umma_bf16_pair(tbase + ((i >> 2) & 1) * 256, ad + 2 * k, bd + 2 * k, idesc, (i > 7) ? 1u : 0u);
+      if (commit_every && k == 3 && ((i >> 2) % commit_every) == commit_every - 1) umma_commit_pair(&rot[(i >> 2) & 7], (uint16_t)mask);
     }
     umma_commit_pair(&bar, 1);
     long long t1 = clock64();
@@ -193,11 +196,20 @@ int main() {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
-    cudaLaunchKernelEx(&lc, k_mma_pair, n, out);
+    cudaLaunchKernelEx(&lc, k_mma_pair, n, out, 0, 3);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
     printf("pair mma M=256 N=256 n=%4d: issue %.1f clk/mma, complete %.1f clk/mma (ideal 128)  %s\n", n, (double)h[0] / n,
            (double)h[1] / n, cudaGetErrorString(e));
+    if (n == 4096) {
+      for (int mask : {1, 3}) for (int every : {1, 2}) {
+        cudaLaunchKernelEx(&lc, k_mma_pair, n, out, every, mask);
+        e = cudaDeviceSynchronize();
+        cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("pair mma + commit(mask %d) every %d x 4 MMAs: complete %.1f clk/mma (ideal 128)  %s\n", mask, every,
+               (double)h[1] / n, cudaGetErrorString(e));
+      }
+    }
   }
   cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   for (int group : {1, 2, 4, 8, 16, 1024}) {

@@ -105,14 +105,26 @@ __global__ void __launch_bounds__(128, 1) k_ring_pair(const uint8_t* src, int to
         for (int c = 0; c < n_st; ++c) {
           if (turn == me) {
             if (cfg.timing == 2) mbar_wait(&w_empty[stage], phase ^ 1u); else mbar_wait_cluster(&w_empty[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&w_full[stage], 16384);
-            bulk_g2s(ring + stage * 16384, src + ((size_t)(2 * c + rank) * 16384) % total_bytes, 16384, &w_full[stage]);
+            const uint8_t* g = src + ((size_t)(2 * c + rank) * 16384) % total_bytes;
+            if (cfg.fence == 3) {
+              // direct signalling: both halves complete_tx on the LEADER's barrier
+              if (rank == 0) mbar_arrive_expect_tx(&w_full[stage], 32768);
+              const uint32_t bar_addr = map_to_cta(smem_u32(&w_full[stage]), 0);
+              const uint32_t dst_addr = map_to_cta(smem_u32(ring + stage * 16384), rank);
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_addr),
+                           "l"(g), "r"(16384u), "r"(bar_addr) : "memory");
+            } else {
+              mbar_arrive_expect_tx(&w_full[stage], 16384);
+              bulk_g2s(ring + stage * 16384, g, 16384, &w_full[stage]);
+            }
           }
           if (++turn == cfg.producers) turn = 0;
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
     }
+  } else if (rank != 0 && cfg.fence == 3) {
+    // nothing to relay
   } else if (rank != 0) {
     // relay modes (cfg.fence): 0 = one thread, release.cluster arrive; 1 = one thread, relaxed arrive;
     // 2 = one lane per stage, release arrive
@@ -144,7 +156,7 @@ __global__ void __launch_bounds__(128, 1) k_ring_pair(const uint8_t* src, int to
     const uint32_t idesc = make_idesc(256u, false, false, 256u);
     for (int c = 0; c < n_st; ++c) {
       mbar_wait(&w_full[stage], phase);
-      if (cfg.timing == 2) mbar_wait(&w_peer[stage], phase); else mbar_wait_cluster(&w_peer[stage], phase);
+      if (cfg.fence != 3) { if (cfg.timing == 2) mbar_wait(&w_peer[stage], phase); else mbar_wait_cluster(&w_peer[stage], phase); }
       tc_fence_after();
       if (cfg.timing) { long long n = clock64(); t_wait += n - t; t = n; }
       const uint32_t a_base = a_addr + (c & 3) * 16384, b_base = r_addr + stage * 16384;
@@ -187,7 +199,7 @@ int main() {
            fence, prod, timing, (double)h[0] / chunks, (double)h[1] / chunks, (double)h[2] / chunks, cudaGetErrorString(e));
   }
   cudaFuncSetAttribute(k_ring_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  for (int stages : {4, 8}) for (int prod : {1}) for (int relay : {0, 1, 2}) for (int timing : {1, 2}) {
+  for (int stages : {4, 8}) for (int prod : {1}) for (int relay : {0, 1, 2}) for (int timing : {2}) {  // relay 3 (direct remote signalling) faults
     Cfg cfg{stages, 1, relay, prod, chunks, timing};
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(148); lc.blockDim = dim3(128); lc.dynamicSmemBytes = 200 * 1024; lc.stream = 0;
