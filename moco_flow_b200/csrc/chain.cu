@@ -14,6 +14,11 @@
 // The layer program (which chunks feed which accumulator columns, which epilogue follows) is a table
 // built by the host shim, so the same kernel runs NeRF / NoF forward and their backward dX chains.
 //
+// Width 256 runs on CTA pairs (template C == 2, cluster of two, tcgen05 cta_group::2): the leader CTA's MMA thread
+// issues M=256 instructions over both CTAs' tiles, each CTA streams only its 128-row half of every [256 x 64] weight
+// tile, the peer relays its ring's "full" barriers to the leader, the leader's commits are multicast to both CTAs.
+// Cross-CTA arrivals are relaxed on purpose (they carry control only).
+//
 // Reference semantics: models/nerf.py:61-102, models/nof.py:55-85, models/embedding.py:42-46.
 #include <cuda_runtime.h>
 #include <stdint.h>
