@@ -231,10 +231,18 @@ __device__ __forceinline__ void nof_quat_backward(const float* h9, const float* 
 // C = CTAs per cluster.  C == 2: the two CTAs of a pair run tcgen05 cta_group::2 -- the leader's MMA thread issues
 // M=256 instructions over both CTAs' tiles, every CTA streams only its half of each weight chunk (the N split of
 // the B operand), which halves the L2 -> shared-memory weight traffic per tile and doubles the ring's depth in time.
-template <int W, int C>
+// kBwd selects the program family the instantiation can run (forward: PE / dense prologue, bias-ReLU / head
+// epilogues; backward: head-gradient prologues, mask / PE-Jacobian epilogues): each kernel carries half the code.
+// kSave: the launch writes training saves (operand images, ReLU masks, head values); inference instantiations carry
+// none of that code.  The in-kernel cycle counters exist only in builds with -DMCF_TIMING (scripts/chain_timing.py).
+template <int W, int C, bool kBwd, bool kSave>
 __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ mcf_chain_params_t p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+#ifdef MCF_TIMING
   const bool timing = p.timing != nullptr;
+#else
+  constexpr bool timing = false;
+#endif
   unsigned long long tacc[4] = {0ull, 0ull, 0ull, 0ull};
   const long long t_kernel0 = timing ? clock64() : 0;
   using L = Smem<W>;
@@ -467,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       if (C == 1 && tile >= n_tiles) break;
       const bool tile_ok = tile < n_tiles;                     // false: a pair's padding tile (no loads/stores)
       const long long tile_r = tile_ok ? tile : n_tiles - 1;   // tile index for reads
-      const bool saving = p.save != nullptr && tile_ok;
+      const bool saving = kSave && p.save != nullptr && tile_ok;
       const long long m = tile * MCF_TILE_ROWS + row;
       const bool valid = m < p.n_rows;
       const long long mc = valid ? m : (p.n_rows - 1);
@@ -486,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       }
 
       // ------------------------- prologue: build the first operand -------------------------
-      if (p.prologue == MCF_PRO_PE_XYZ) {
+      if (!kBwd && p.prologue == MCF_PRO_PE_XYZ) {
         float x[3] = {0.f, 0.f, 0.f};
         if (valid) { x[0] = p.xyz[m * 3 + 0]; x[1] = p.xyz[m * 3 + 1]; x[2] = p.xyz[m * 3 + 2]; }
         // channel order of models/embedding.py:42-46: [x | w0 sin(f0 x) | w0 cos(f0 x) | w1 sin(f1 x) | ...]
@@ -525,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           v.z = pack_bf16x2(ch[c8 * 8 + 4], ch[c8 * 8 + 5]); v.w = pack_bf16x2(ch[c8 * 8 + 6], ch[c8 * 8 + 7]);
           *reinterpret_cast<uint4*>(x0buf + sw128_off(row, c8)) = v;
         }
-      } else if (p.prologue == MCF_PRO_DENSE) {
+      } else if (!kBwd && p.prologue == MCF_PRO_DENSE) {
         const float* src = p.dense + mc * p.dense_stride;
         for (int c8 = 0; c8 < 8; ++c8) {
           float f[8];
@@ -539,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
           *reinterpret_cast<uint4*>(x0buf + sw128_off(row, c8)) = v;
         }
-      } else if (p.prologue == MCF_PRO_B_NERF) {
+      } else if (kBwd && p.prologue == MCF_PRO_B_NERF) {
         // backward through rgb = sigmoid(W_rgb he + b) and he = relu(.)   (models/nerf.py:98-99)
         float4 g = valid ? *reinterpret_cast<const float4*>(p.g_out + m * 4) : make_float4(0, 0, 0, 0);
         float4 o = valid ? *reinterpret_cast<const float4*>(p.fwd_out + m * 4) : make_float4(0, 0, 0, 0);
@@ -570,7 +578,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           }
           store_h32(hbuf, row, c0, f);
         }
-      } else {  // MCF_PRO_B_NOF
+      } else if (kBwd) {  // MCF_PRO_B_NOF
         float g[3] = {0.f, 0.f, 0.f}, hs[12];
 #pragma unroll
         for (int j = 0; j < 12; ++j) hs[j] = 0.f;
@@ -628,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         // the prologue's operand is itself needed by the weight-gradient GEMM: store its image
         named_bar_sync(1 + s, 128);
         if (gtid == 0) {
-          const bool fwd = p.prologue == MCF_PRO_PE_XYZ || p.prologue == MCF_PRO_DENSE;
+          const bool fwd = !kBwd;
           const uint32_t nbytes = fwd ? kBlk : (p.prologue == MCF_PRO_B_NERF ? (uint32_t)(W / 2 / 64) * kBlk : kBlk);
           bulk_s2g(save_tile + p.x0_save_off, fwd ? x0buf : hbuf, nbytes);
           bulk_commit();
@@ -642,8 +650,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       for (int r = 0; r < p.n_rounds; ++r) {
         const mcf_round_t rd = tab.rounds[r];
         const float* bias_p = (rd.raybias >= 0) ? (p.raybias[rd.raybias] + ray * rd.n_out) : (p.consts + rd.const_off);
-        const bool is_bias_epi = rd.epi == MCF_EPI_RELU || rd.epi == MCF_EPI_RELU_SIGMA || rd.epi == MCF_EPI_LINEAR;
-        const bool is_mask_epi = rd.epi == MCF_EPI_B_MASK || rd.epi == MCF_EPI_B_MASK_SIGMA;
+        const bool is_bias_epi = !kBwd && (rd.epi == MCF_EPI_RELU || rd.epi == MCF_EPI_RELU_SIGMA || rd.epi == MCF_EPI_LINEAR);
+        const bool is_mask_epi = kBwd && (rd.epi == MCF_EPI_B_MASK || rd.epi == MCF_EPI_B_MASK_SIGMA);
         // operands that do not depend on the accumulator are fetched before waiting for the tensor core
         float b0[32];
         uint32_t mwords[8];
@@ -670,8 +678,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         }
         const uint32_t t_acc = t_row + rd.acc_col;
 
-        if (rd.epi == MCF_EPI_RELU || rd.epi == MCF_EPI_RELU_SIGMA || rd.epi == MCF_EPI_LINEAR) {
-          const bool want_mask = p.masks != nullptr && rd.mask_off != kNone && tile_ok;
+        if (!kBwd && (rd.epi == MCF_EPI_RELU || rd.epi == MCF_EPI_RELU_SIGMA || rd.epi == MCF_EPI_LINEAR)) {
+          const bool want_mask = kSave && p.masks != nullptr && rd.mask_off != kNone && tile_ok;
           uint32_t* mk = want_mask ? (p.masks + tile * p.mask_tile_words + rd.mask_off + row) : nullptr;
           float sig = 0.f;
           float b1[32];
@@ -709,7 +717,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             st.sigma = sig + __ldg(p.consts + rd.aux_off + rd.n_out);
             if (p.sigma_col == 0 && valid) p.out[m * p.out_stride] = st.sigma;  // sigma-only program
           }
-        } else if (rd.epi == MCF_EPI_NERF_RGB) {
+        } else if (!kBwd && rd.epi == MCF_EPI_NERF_RGB) {
           const int nhe = rd.n_out;
           const float* wrgb = p.consts + rd.aux_off;  // [3][nhe] then b_rgb[3]
           float a0 = __ldg(wrgb + 3 * nhe + 0), a1 = __ldg(wrgb + 3 * nhe + 1), a2 = __ldg(wrgb + 3 * nhe + 2);
@@ -736,7 +744,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
 #pragma unroll
             for (int j = 0; j < 32; ++j) a2 = fmaf(f[j], w0[j], a2);
             if (saving) store_h32(hbuf, row, c0, f);
-            if (p.masks && rd.mask_off != kNone && tile_ok)
+            if (kSave && p.masks && rd.mask_off != kNone && tile_ok)
               p.masks[tile * p.mask_tile_words + rd.mask_off + (c0 >> 5) * 128 + row] = word;
           }
           if (valid) {
@@ -747,7 +755,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             o.w = st.sigma;
             *reinterpret_cast<float4*>(p.out + m * 4) = o;
           }
-        } else if (rd.epi == MCF_EPI_NOF_HEAD) {
+        } else if (!kBwd && rd.epi == MCF_EPI_NOF_HEAD) {
           uint32_t v[16];
           tmem_ld16(t_acc, v);
           tmem_ld_wait();
@@ -762,14 +770,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           }
           if (valid) {
             p.out[m * 3 + 0] = o[0]; p.out[m * 3 + 1] = o[1]; p.out[m * 3 + 2] = o[2];
-            if (p.head_save) {
+            if (kSave && p.head_save) {
               float4* hp = reinterpret_cast<float4*>(p.head_save + m * 12);
               hp[0] = make_float4(h9[0], h9[1], h9[2], h9[3]);
               hp[1] = make_float4(h9[4], h9[5], h9[6], h9[7]);
               hp[2] = make_float4(h9[8], x[0], x[1], x[2]);
             }
           }
-        } else if (rd.epi == MCF_EPI_B_MASK || rd.epi == MCF_EPI_B_MASK_SIGMA || rd.epi == MCF_EPI_B_LINEAR) {
+        } else if (kBwd && (rd.epi == MCF_EPI_B_MASK || rd.epi == MCF_EPI_B_MASK_SIGMA || rd.epi == MCF_EPI_B_LINEAR)) {
           for (int c0 = 0; c0 < rd.n_out; c0 += 32) {
             uint32_t v[32];
             float f[32];
@@ -792,7 +800,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             for (int j = 0; j < 32; ++j) f[j] = ((word >> j) & 1u) ? f[j] : 0.f;
             store_h32(hbuf, row, c0, f);
           }
-        } else if (rd.epi == MCF_EPI_B_DPE) {
+        } else if (kBwd && rd.epi == MCF_EPI_B_DPE) {
           // d_xyz += J_PE(x)^T dPE, with sin/cos taken from the saved first-layer operand image
           const uint8_t* x0img = reinterpret_cast<const uint8_t*>(p.fwd_save) + tile_r * p.fwd_save_tile_bytes + p.fwd_x0_off;
           float pe[64];
@@ -1033,38 +1041,47 @@ int mcf_chain_launch(const mcf_chain_params_t* pp, cudaStream_t stream) {
   int cap = (p.max_ctas > 0 ? p.max_ctas : n_sm) / ctas;
   if (cap < 1) cap = 1;
   int grid = (int)(n_units < cap ? n_units : cap) * ctas;
+  const bool bwd = p.prologue == MCF_PRO_B_NERF || p.prologue == MCF_PRO_B_NOF;
   cudaError_t e;
+  const void* fn = nullptr;
+  int smem = 0;
+  const bool save = bwd || p.save != nullptr || p.masks != nullptr || p.head_save != nullptr;
+#define MCF_PICK(W_, C_)                                                                                  \
+  (bwd ? (const void*)mcf::k_chain<W_, C_, true, true>                                                   \
+       : (save ? (const void*)mcf::k_chain<W_, C_, false, true> : (const void*)mcf::k_chain<W_, C_, false, false>))
   if (p.width == 256 && ctas == 2) {
-    const int smem = (int)mcf::Smem<256>::total;
-    e = cudaFuncSetAttribute(mcf::k_chain<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(mcf::kThreads);
-    cfg.dynamicSmemBytes = (size_t)smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, mcf::k_chain<256, 2>, p);
-    if (e != cudaSuccess) return (int)e;
+    fn = MCF_PICK(256, 2);
+    smem = (int)mcf::Smem<256>::total;
   } else if (p.width == 256) {
-    const int smem = (int)mcf::Smem<256>::total;
-    e = cudaFuncSetAttribute(mcf::k_chain<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    mcf::k_chain<256, 1><<<grid, mcf::kThreads, smem, stream>>>(p);
+    fn = MCF_PICK(256, 1);
+    smem = (int)mcf::Smem<256>::total;
   } else if (p.width == 128) {
-    const int smem = (int)mcf::Smem<128>::total;
-    e = cudaFuncSetAttribute(mcf::k_chain<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    mcf::k_chain<128, 1><<<grid, mcf::kThreads, smem, stream>>>(p);
+    fn = MCF_PICK(128, 1);
+    smem = (int)mcf::Smem<128>::total;
   } else {
     return MCF_ERR_UNSUPPORTED;
   }
+#undef MCF_PICK
+#ifndef MCF_TIMING
+  if (p.timing != nullptr) return MCF_ERR_UNSUPPORTED;   // cycle counters need a -DMCF_TIMING build
+#endif
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(mcf::kThreads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  void* args[1] = {const_cast<mcf_chain_params_t*>(&p)};
+  e = cudaLaunchKernelExC(&cfg, fn, args);
+  if (e != cudaSuccess) return (int)e;
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

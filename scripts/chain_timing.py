@@ -5,7 +5,27 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+
+
+def _build_timing_library() -> str:
+    """The cycle counters are compiled in only with -DMCF_TIMING: build that variant next to the product library."""
+    import subprocess
+    from moco_flow_b200 import build as B
+    B.build()
+    csrc = B.CSRC
+    obj = os.path.join(csrc, "chain_timing.o")
+    lib = os.path.join(csrc, "libmoco_flow_b200_timing.so")
+    nvcc = B._nvcc()
+    subprocess.run([nvcc, *B.ARCH, *B.COMMON, "-DMCF_TIMING", "-c", os.path.join(csrc, "chain.cu"), "-o", obj], check=True)
+    others = [os.path.join(csrc, u.replace(".cu", ".o")) for u, _ in B.UNITS if u != "chain.cu"]
+    subprocess.run([nvcc, *B.ARCH, "-shared", "-o", lib, obj, *others], check=True)
+    return lib
+
+
+_TIMING_LIB = _build_timing_library()
 import torch  # noqa: E402
+from moco_flow_b200 import _lib as _L  # noqa: E402
+_L.LIB_PATH = _TIMING_LIB   # before the first call loads the library
 
 import bench  # noqa: E402
 import moco_flow_b200 as mf  # noqa: E402

@@ -70,8 +70,13 @@ __global__ void __launch_bounds__(128, 1) k_copy(const uint8_t* src, int total_b
 
 
 // `nthr` issuing threads (one per warp), each keeping `depth` copies of `bytes` in flight into its own smem region
+__device__ __forceinline__ void bulk_g2s_cta(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 __global__ void __launch_bounds__(256, 1) k_copy_mt(const uint8_t* src, int total_bytes, int bytes, int depth, int iters,
-                                                    int nthr, unsigned long long* out) {
+                                                    int nthr, unsigned long long* out, int cta_form = 0) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar[8][8];
   if (threadIdx.x == 0) {
@@ -91,8 +96,12 @@ __global__ void __launch_bounds__(256, 1) k_copy_mt(const uint8_t* src, int tota
       if (i < n) {
         mbar_arrive_expect_tx(&bar[w][s], bytes);
         long long a = clock64();
-        bulk_g2s(smem + (size_t)(w * depth + s) * bytes, src + (size_t)(((long long)(i * nthr + w) * bytes) % total_bytes), bytes,
-                 &bar[w][s]);
+        if (cta_form)
+          bulk_g2s_cta(smem + (size_t)(w * depth + s) * bytes, src + (size_t)(((long long)(i * nthr + w) * bytes) % total_bytes),
+                       bytes, &bar[w][s]);
+        else
+          bulk_g2s(smem + (size_t)(w * depth + s) * bytes, src + (size_t)(((long long)(i * nthr + w) * bytes) % total_bytes), bytes,
+                   &bar[w][s]);
         t_issue += clock64() - a;
       }
     }
@@ -235,6 +244,14 @@ int main() {
     }
   }
   cudaFuncSetAttribute(k_copy_mt, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  for (int form : {0, 1}) for (int nthr : {1, 4}) {
+    k_copy_mt<<<148, 256, 200 * 1024>>>(src, total, 16384, 2, 8, nthr, out, form);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+    double n = (double)(total / 16384 * 8 / nthr) * nthr;
+    printf("copy form=%s threads=%d: %.1f B/clk/SM, issue instr %llu clk  %s\n", form ? "shared::cta" : "shared::cluster", nthr,
+           n * 16384 / (double)h[0], h[1], cudaGetErrorString(e));
+  }
   for (int grid : {1, 148}) {
     for (int bytes : {4096, 16384, 32768, 65536}) {
       for (int nthr : {1, 2, 4}) {
