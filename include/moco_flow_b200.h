@@ -206,6 +206,9 @@ typedef struct {
   /* width 256 only: non-zero launches clusters of two CTAs that run tcgen05 cta_group::2 (one M=256 MMA stream over
    * both CTAs' tiles; every CTA fetches only its half of each weight chunk) */
   int32_t cta_pair;
+  /* 0: NeRF program (sigma / rgb heads), 1: NoF program (flow head).  Selects a kernel instantiation that carries only
+   * that family's prologues and epilogues; a program of the other family fails with the device error flag. */
+  int32_t program_kind;
 } mcf_chain_params_t;
 
 int mcf_chain_launch(const mcf_chain_params_t* params_host, cudaStream_t stream);

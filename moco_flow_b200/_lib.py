@@ -56,7 +56,7 @@ class ChainParams(C.Structure):
         ("fwd_mask_tile_words", _i64), ("fwd_x0_off", _u32), ("fwd_he_off", _u32),
         ("d_xyz", _vp), ("d_head", _vp), ("rayfeat", _vp), ("rayfeat_stride", _i32), ("rayfeat_dim", _i32),
         ("extra_save_off", _u32), ("dhead_save_off", _u32), ("max_ctas", _i32),
-        ("timing", _vp), ("cta_pair", _i32),
+        ("timing", _vp), ("cta_pair", _i32), ("program_kind", _i32),
     ]
 
 

@@ -235,7 +235,8 @@ __device__ __forceinline__ void nof_quat_backward(const float* h9, const float* 
 // epilogues; backward: head-gradient prologues, mask / PE-Jacobian epilogues): each kernel carries half the code.
 // kSave: the launch writes training saves (operand images, ReLU masks, head values); inference instantiations carry
 // none of that code.  The in-kernel cycle counters exist only in builds with -DMCF_TIMING (scripts/chain_timing.py).
-template <int W, int C, bool kBwd, bool kSave>
+// kNoF: NoF program (flow head, quaternion transform) vs NeRF program (sigma / rgb heads).
+template <int W, int C, bool kBwd, bool kSave, bool kNoF>
 __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ mcf_chain_params_t p) {
   extern __shared__ __align__(1024) uint8_t smem[];
 #ifdef MCF_TIMING
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
           *reinterpret_cast<uint4*>(x0buf + sw128_off(row, c8)) = v;
         }
-      } else if (kBwd && p.prologue == MCF_PRO_B_NERF) {
+      } else if (kBwd && !kNoF && p.prologue == MCF_PRO_B_NERF) {
         // backward through rgb = sigmoid(W_rgb he + b) and he = relu(.)   (models/nerf.py:98-99)
         float4 g = valid ? *reinterpret_cast<const float4*>(p.g_out + m * 4) : make_float4(0, 0, 0, 0);
         float4 o = valid ? *reinterpret_cast<const float4*>(p.fwd_out + m * 4) : make_float4(0, 0, 0, 0);
@@ -578,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           }
           store_h32(hbuf, row, c0, f);
         }
-      } else if (kBwd) {  // MCF_PRO_B_NOF
+      } else if (kBwd && kNoF && p.prologue == MCF_PRO_B_NOF) {
         float g[3] = {0.f, 0.f, 0.f}, hs[12];
 #pragma unroll
         for (int j = 0; j < 12; ++j) hs[j] = 0.f;
@@ -613,6 +614,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         store_h8(hbuf, row, 8, v);
 #pragma unroll
         for (int c8 = 2; c8 < 8; ++c8) store_h8(hbuf, row, c8 * 8, make_uint4(0, 0, 0, 0));
+      } else {
+        if (gtid == 0) atomicExch(&g_mcf_device_error, 0xBADF0000u | (uint32_t)p.prologue);
       }
       if (saving && p.extra_save_off != kNone && p.rayfeat != nullptr) {
         // per-ray feature columns as an image block, written straight to the save record
@@ -686,7 +689,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           auto do_chunk = [&](int c0, uint32_t (&v)[32], const float (&b)[32]) {
             if (rd.epi == MCF_EPI_LINEAR) {
               bias_act_store32<false, false>(hbuf, row, c0, v, b);
-            } else if (rd.epi == MCF_EPI_RELU_SIGMA) {
+            } else if (!kNoF && rd.epi == MCF_EPI_RELU_SIGMA) {
               float ws[32];
               load32f(p.consts + rd.aux_off + c0, ws);
 #pragma unroll
@@ -713,11 +716,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             if (more) tmem_ld32(t_acc + c0 + 64, va);
             do_chunk(c0 + 32, vb, b1);
           }
-          if (rd.epi == MCF_EPI_RELU_SIGMA) {
+          if (!kNoF && rd.epi == MCF_EPI_RELU_SIGMA) {
             st.sigma = sig + __ldg(p.consts + rd.aux_off + rd.n_out);
             if (p.sigma_col == 0 && valid) p.out[m * p.out_stride] = st.sigma;  // sigma-only program
           }
-        } else if (!kBwd && rd.epi == MCF_EPI_NERF_RGB) {
+        } else if (!kBwd && !kNoF && rd.epi == MCF_EPI_NERF_RGB) {
           const int nhe = rd.n_out;
           const float* wrgb = p.consts + rd.aux_off;  // [3][nhe] then b_rgb[3]
           float a0 = __ldg(wrgb + 3 * nhe + 0), a1 = __ldg(wrgb + 3 * nhe + 1), a2 = __ldg(wrgb + 3 * nhe + 2);
@@ -755,7 +758,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             o.w = st.sigma;
             *reinterpret_cast<float4*>(p.out + m * 4) = o;
           }
-        } else if (!kBwd && rd.epi == MCF_EPI_NOF_HEAD) {
+        } else if (!kBwd && kNoF && rd.epi == MCF_EPI_NOF_HEAD) {
           uint32_t v[16];
           tmem_ld16(t_acc, v);
           tmem_ld_wait();
@@ -787,7 +790,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             for (int j = 0; j < 8; ++j)
               if (j == (c0 >> 5)) word = mwords[j];
             tmem_ld_wait();
-            if (rd.epi == MCF_EPI_B_MASK_SIGMA) {
+            if (!kNoF && rd.epi == MCF_EPI_B_MASK_SIGMA) {
               float ws[32];
               load32f(p.consts + rd.aux_off + c0, ws);
 #pragma unroll
@@ -835,6 +838,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           if (rd.aux_off == 1u && valid && p.d_xyz) {
             p.d_xyz[m * 3 + 0] = st.dx[0]; p.d_xyz[m * 3 + 1] = st.dx[1]; p.d_xyz[m * 3 + 2] = st.dx[2];
           }
+        } else {
+          // an epilogue this instantiation was not compiled for: refuse loudly instead of skipping it
+          if (gtid == 0) atomicExch(&g_mcf_device_error, 0xBADE0000u | (uint32_t)rd.epi);
         }
 
         tc_fence_before();
@@ -1046,9 +1052,13 @@ int mcf_chain_launch(const mcf_chain_params_t* pp, cudaStream_t stream) {
   const void* fn = nullptr;
   int smem = 0;
   const bool save = bwd || p.save != nullptr || p.masks != nullptr || p.head_save != nullptr;
-#define MCF_PICK(W_, C_)                                                                                  \
-  (bwd ? (const void*)mcf::k_chain<W_, C_, true, true>                                                   \
-       : (save ? (const void*)mcf::k_chain<W_, C_, false, true> : (const void*)mcf::k_chain<W_, C_, false, false>))
+#define MCF_PICK2(W_, C_, N_)                                                                             \
+  (bwd ? (const void*)mcf::k_chain<W_, C_, true, true, N_>                                                \
+       : (save ? (const void*)mcf::k_chain<W_, C_, false, true, N_> : (const void*)mcf::k_chain<W_, C_, false, false, N_>))
+#define MCF_PICK(W_, C_) (nof ? MCF_PICK2(W_, C_, true) : MCF_PICK2(W_, C_, false))
+  const bool nof = p.program_kind == 1;
+  if (p.program_kind != 0 && p.program_kind != 1) return MCF_ERR_BAD_ARG;
+  if ((p.prologue == MCF_PRO_B_NOF) != (bwd && nof)) return MCF_ERR_BAD_ARG;
   if (p.width == 256 && ctas == 2) {
     fn = MCF_PICK(256, 2);
     smem = (int)mcf::Smem<256>::total;
@@ -1061,6 +1071,7 @@ int mcf_chain_launch(const mcf_chain_params_t* pp, cudaStream_t stream) {
   } else {
     return MCF_ERR_UNSUPPORTED;
   }
+#undef MCF_PICK2
 #undef MCF_PICK
 #ifndef MCF_TIMING
   if (p.timing != nullptr) return MCF_ERR_UNSUPPORTED;   // cycle counters need a -DMCF_TIMING build

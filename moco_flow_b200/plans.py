@@ -41,6 +41,7 @@ class Plan:
     mask_tile_words: int = 0
     offsets: Dict[str, int] = field(default_factory=dict)   # named save / mask / const offsets
     n_raybias: int = 0
+    kind: int = 0          # 0: NeRF program, 1: NoF program (selects the kernel instantiation)
 
 
 class _Builder:
@@ -108,14 +109,14 @@ class _Builder:
         self.mask_words += _ceil(n_cols, 32) * 128
         return off
 
-    def finish(self, n_raybias: int = 0) -> Plan:
+    def finish(self, n_raybias: int = 0, kind: int = 0) -> Plan:
         self.chunks = [tuple(c) for c in self.chunks]
         assert len(self.chunks) <= 128 and len(self.rounds) <= 24 and len(self.names) <= 32, \
             (len(self.chunks), len(self.rounds), len(self.names))
         return Plan(self.width, list(self.names),
                     np.array(self.pack, dtype=L.PACK_DT), np.array(self.chunks, dtype=L.CHUNK_DT),
                     np.array(self.rounds, dtype=L.ROUND_DT), self.wbytes, max(self.nconst, 4),
-                    self.save_bytes, self.mask_words, dict(self.offsets), n_raybias)
+                    self.save_bytes, self.mask_words, dict(self.offsets), n_raybias, kind)
 
 
 def _check_common(W: int, cx: int) -> None:
@@ -224,7 +225,7 @@ def nof_forward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: i
     b.round(L.EPI_NOF_HEAD, 16, 0, c0, const_off=boff)
     if rb > 4:
         raise ValueError("at most 4 folded layers (first + 3 skips) are supported")
-    return b.finish(n_raybias=rb)
+    return b.finish(n_raybias=rb, kind=1)
 
 
 def folded_layers(D: int, skips: Sequence[int]) -> List[int]:
@@ -388,7 +389,7 @@ def nof_backward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: 
         b.chunk(img, 1, 0, 1, 128, nh * 128, init=True)
     b.round(L.EPI_B_MASK, W, 0, c0, save_off=b.save_slot(f"dy{D}", nkb), mask_off=fwd.offsets[f"mask_h{D}"])
     _bwd_trunk(b, fwd, D, W, cx, tuple(skips), extra_dim, "nof_encoding", need_dx)
-    return b.finish()
+    return b.finish(kind=1)
 
 
 def nerf_grad_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: int, shapes: Dict[str, tuple],
