@@ -97,7 +97,19 @@ __global__ void __launch_bounds__(128, 1) k_ring_pair(const uint8_t* src, int to
   tc_fence_before(); __syncthreads(); cluster_sync_all(); tc_fence_after();
   const int S = cfg.stages;
   const int n_st = cfg.chunks / 2;   // stages per CTA (each covers two of the single-CTA kernel's chunks)
-  if (warp != 1) {
+  if (rank != 0 && cfg.fence == 4 && warp >= 1) {
+    // relay mode 4: three relay threads (lane 0 of warps 1..3 of the peer), stage sequence split round-robin
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int c = 0; c < n_st; ++c) {
+        if (c % 3 == warp - 1) {
+          mbar_wait(&w_full[stage], phase);
+          mbar_arrive_cluster_relaxed(map_to_cta(smem_u32(&w_peer[stage]), 0));
+        }
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp != 1) {
     if (lane == 0) {
       const int me = warp == 0 ? 0 : warp - 1;
       if (me < cfg.producers) {
@@ -199,7 +211,7 @@ int main() {
            fence, prod, timing, (double)h[0] / chunks, (double)h[1] / chunks, (double)h[2] / chunks, cudaGetErrorString(e));
   }
   cudaFuncSetAttribute(k_ring_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  for (int stages : {4, 8}) for (int prod : {1}) for (int relay : {0, 1, 2}) for (int timing : {2}) {  // relay 3 (direct remote signalling) faults
+  for (int stages : {4, 8}) for (int prod : {1}) for (int relay : {1, 4}) for (int timing : {2}) {  // relay 3 (direct remote signalling) faults
     Cfg cfg{stages, 1, relay, prod, chunks, timing};
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(148); lc.blockDim = dim3(128); lc.dynamicSmemBytes = 200 * 1024; lc.stream = 0;

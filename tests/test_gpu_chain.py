@@ -167,6 +167,33 @@ def test_nerf_cta_pair_matches_single(dev, rows, monkeypatch):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-5 * float(a.abs().max()) + 1e-12)
 
 
+def test_wrong_program_family_fails_loudly(dev, golden_dir):
+    """Kernels are instantiated per program family; a NoF program launched as a NeRF one must raise the device flag
+    (forward: the flow-head epilogue is not compiled in) or be refused (backward), never silently skip work."""
+    import moco_flow_b200 as mf
+    from moco_flow_b200 import _lib as L
+    g = dict(np.load(os.path.join(golden_dir, "modules.npz")))
+    m = mf.NoF(4, 128, 33, [2], "ind", 33, True)
+    m.load_state_dict(orc.make_nof_params(orc.C2F_NOF, 21))
+    m = m.to(dev)
+    x, xyz = T(g["nof_in"]).to(dev), T(g["nof_xyz"]).to(dev)
+    with torch.no_grad():
+        good = m(x, xyz)
+        torch.cuda.synchronize()
+        assert L.device_error_flag() == 0
+        for pp in m._plan_cache().values():
+            pp.plan.kind = 0
+        m(x, xyz)
+        torch.cuda.synchronize()
+        flag = L.device_error_flag()
+        assert (flag & 0xFFFF0000) == 0xBADE0000 and (flag & 0xFFFF) == L.EPI_NOF_HEAD, hex(flag)
+        for pp in m._plan_cache().values():
+            pp.plan.kind = 1
+        again = m(x, xyz)
+        torch.cuda.synchronize()
+    assert L.device_error_flag() == 0 and torch.equal(good, again)
+
+
 def _build_cuda_models(dev, nerfs, nofs, nerf_pes, nof_pes):
     import moco_flow_b200 as mf
     from tests.helpers import pe_module
