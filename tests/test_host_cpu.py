@@ -129,3 +129,17 @@ def test_no_cpu_fallback():
         n(torch.zeros(4, 68))
     with pytest.raises(RuntimeError):
         mf.Embedding(3, 2)(torch.zeros(4, 3))
+
+
+def test_plans_carry_their_program_family():
+    """The C ABI picks a kernel instantiation from ``program_kind`` (0 NeRF, 1 NoF): forward and backward plans of a
+    module must agree, and the offsets of the struct fields the launcher reads must exist in the ctypes mirror."""
+    nf = P.nerf_forward_plan(8, 256, 63, (4,), 5, False, True)
+    nb = P.nerf_backward_plan(8, 256, 63, (4,), 5, True, nf)
+    of = P.nof_forward_plan(4, 128, 33, (2,), 33, True, True)
+    ob = P.nof_backward_plan(4, 128, 33, (2,), 33, True, True, of)
+    assert (nf.kind, nb.kind, of.kind, ob.kind) == (0, 0, 1, 1)
+    assert all(int(e) < 16 for e in nf.rounds["epi"]) and all(int(e) >= 16 for e in nb.rounds["epi"])
+    assert int(of.rounds["epi"][-1]) == L.EPI_NOF_HEAD
+    names = [f[0] for f in L.ChainParams._fields_]
+    assert names[-2:] == ["cta_pair", "program_kind"]
