@@ -49,11 +49,54 @@ def feat_view(feat: torch.Tensor) -> torch.Tensor:
     return feat
 
 
+# Per-call memo (rendering.render_rays opens it): within one render call the per-ray embeddings and the folded per-ray
+# biases depend only on (rays, weights), not on the sample positions, so the coarse and the fine pass and the repeated
+# evaluations of one flow network share them -- 6 distinct results instead of 22 launches in a training step.
+_MEMO = None
+
+
+class call_memo:
+    """Context manager: memoise per-ray features / folded biases for the duration of one rendering call."""
+
+    def __enter__(self):
+        global _MEMO
+        self.outer = _MEMO
+        if _MEMO is None:
+            _MEMO = {}
+        return self
+
+    def __exit__(self, *exc):
+        global _MEMO
+        if self.outer is None:
+            _MEMO = None
+        return False
+
+
+def memoised(key: tuple, keep_alive: tuple, make):
+    """``make()`` once per key while a ``call_memo`` is open; ``keep_alive`` pins the tensors whose addresses are in the key."""
+    if _MEMO is None:
+        return make()
+    hit = _MEMO.get(key)
+    if hit is None:
+        hit = (make(), keep_alive)
+        _MEMO[key] = hit
+    return hit[0]
+
+
+def _tkey(t: torch.Tensor) -> tuple:
+    return (t.data_ptr(), t._version, tuple(t.shape), t.stride())
+
+
 def fold_bias(weight: torch.Tensor, col_off: int, bias: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
     """Per-row bias b + W[:, col_off:col_off+E] feat^T for per-ray constant input columns."""
-    import ctypes as C
     feat = feat_view(feat.detach())
     weight, bias = weight.detach(), bias.detach()
+    key = ("fold", _tkey(weight), col_off, _tkey(bias), _tkey(feat))
+    return memoised(key, (weight, bias, feat), lambda: _fold_bias(weight, col_off, bias, feat))
+
+
+def _fold_bias(weight: torch.Tensor, col_off: int, bias: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
+    import ctypes as C
     R, E = feat.shape
     N = weight.shape[0]
     out = torch.empty(R, N, device=feat.device)

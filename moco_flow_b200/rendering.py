@@ -35,8 +35,11 @@ def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5, u=None):
 
 
 def _ray_embedding(embedding, values):
-    """Per-ray embedded feature (R, C) -- evaluated once per ray, never repeated per sample."""
-    return embedding(values.detach().contiguous())
+    """Per-ray embedded feature (R, C) -- evaluated once per ray, never repeated per sample, and once per rendering
+    call for the same (embedding, values) pair."""
+    from .mlp import memoised, _tkey
+    key = ("emb", id(embedding), tuple(float(w) for w in getattr(embedding, "weights", ())), _tkey(values))
+    return memoised(key, (values, embedding), lambda: embedding(values.detach().contiguous()))
 
 
 def nof_inference(xyz_, ind_, nof_embeddings, nof_model):
@@ -87,6 +90,16 @@ def render_rays(rays, background, nerf_embeddings, nerf_models, nof_embeddings=N
                 noise_std=1, nerf_activate_type='relu', test_time=False, draws: Optional[Draws] = None,
                 fused_residual_mean: bool = False) -> Dict[str, torch.Tensor]:
     """rendering.py:195-375."""
+    from .mlp import call_memo
+    with call_memo():
+        return _render_rays(rays, background, nerf_embeddings, nerf_models, nof_embeddings, nof_models, chain_local,
+                            chain_global, N_samples, N_importance, use_disp, perturb, noise_std, nerf_activate_type,
+                            test_time, draws, fused_residual_mean)
+
+
+def _render_rays(rays, background, nerf_embeddings, nerf_models, nof_embeddings, nof_models, chain_local, chain_global,
+                 N_samples, N_importance, use_disp, perturb, noise_std, nerf_activate_type, test_time, draws,
+                 fused_residual_mean):
     draws = draws or Draws()
     rays = rays.contiguous()
     R = rays.shape[0]
