@@ -30,7 +30,7 @@ namespace mcf {
 
 constexpr int kThreads = 384;
 constexpr int kMaxStages = 8;
-constexpr int kProducers = 1;  // producer warps (0, then 2, 3).  More than one was measured: no gain, their polling costs issue slots
+constexpr int kProducers = 1;  // producer warps (0, then 2, 3).  Three were measured against one in both ring modes: no gain
 constexpr uint32_t kBlk = MCF_BLOCK_BYTES;
 constexpr int kMaxChunks = 128;
 constexpr int kMaxRounds = 24;
