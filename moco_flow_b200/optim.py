@@ -64,6 +64,10 @@ class FusedAdam(torch.optim.Optimizer):
         m = torch.zeros(total, device=dev)
         v = torch.zeros(total, device=dev)
         step = old["step"] if old is not None else torch.zeros(1, dtype=torch.int64, device=dev)
+        if old is None:   # a loaded state_dict (torch.optim.Adam layout) carries the step count per parameter
+            loaded = [int(float(self.state[p]["step"])) for p in ps if "step" in self.state[p]]
+            if loaded:
+                step.fill_(max(loaded))
         lr_dev = old["lr_dev"] if old is not None else torch.full((1,), float(group["lr"]), device=dev)
         off = 0
         seg_off = []
@@ -84,6 +88,22 @@ class FusedAdam(torch.optim.Optimizer):
         plan = dict(key=key, segs=segs, seg_off=seg_off, m=m, v=v, step=step, lr_dev=lr_dev, lr_host=None)
         self._plans[gi] = plan
         return plan
+
+    def state_dict(self):
+        """Same layout as ``torch.optim.Adam.state_dict()``; the moments are cloned so that a saved file holds one
+        tensor per parameter instead of a view of the flat buffer (which ``torch.save`` would store whole, per view)."""
+        sd = super().state_dict()
+        for st in sd["state"].values():
+            for k, v in list(st.items()):
+                if torch.is_tensor(v):
+                    st[k] = v.detach().clone()
+        return sd
+
+    def load_state_dict(self, state_dict) -> None:
+        """Accepts the state of a ``torch.optim.Adam`` over the same parameters (trainer/base.py:316-321) or of a
+        ``FusedAdam``; the flat moment buffers are rebuilt from it on the next step."""
+        super().load_state_dict(state_dict)
+        self._plans.clear()
 
     def sync_lr(self) -> None:
         """Copies every group's ``lr`` to its device scalar (call after a scheduler step, outside graph capture)."""
