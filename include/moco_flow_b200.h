@@ -288,6 +288,15 @@ int mcf_canvas_scatter(const float* background, long long n_pixels, const long l
                        const float* rgb, const float* depth, const float* opacity, float* img_out, float* depth_out,
                        cudaStream_t stream);
 
+/* ---- SMPL correspondence sampling ---------------------------------------------- */
+/* datasets/moco_flow_dataset.py:121-130: for every query point the nearest of n_verts vertices (what
+ * knn_cuda.KNN(k=1, transpose_mode=True) returns: Euclidean distance and index; first minimum on ties),
+ * inside[q] = dist < thickness, and cano[q] = (trans[ind[q]] @ [x y z 1])[:3] with trans [n_verts][4][4] row-major.
+ * Any of dist / ind / cano / inside may be NULL (trans may be NULL when cano is). */
+int mcf_nearest_vertex(const float* verts, int n_verts, const float* trans, const float* query, long long n_query,
+                       float thickness, float* dist, long long* ind, float* cano, unsigned char* inside,
+                       cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

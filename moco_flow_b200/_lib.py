@@ -73,7 +73,7 @@ EXPORTS = [
     "mcf_abi_version", "mcf_device_error_flag", "mcf_coarse_samples", "mcf_ray_points", "mcf_pe_fwd", "mcf_pe_bwd",
     "mcf_ray_bias", "mcf_composite_fwd", "mcf_composite_bwd", "mcf_sample_pdf", "mcf_masked_l1_fwd",
     "mcf_masked_l1_bwd", "mcf_pack", "mcf_chain_launch", "mcf_dw_gemm", "mcf_dw_gemm_batch", "mcf_unpack",
-    "mcf_unpack_accumulate", "mcf_colsum", "mcf_adam_step", "mcf_make_rays", "mcf_canvas_scatter",
+    "mcf_unpack_accumulate", "mcf_colsum", "mcf_adam_step", "mcf_make_rays", "mcf_canvas_scatter", "mcf_nearest_vertex",
 ]
 
 _lib = None

@@ -27,6 +27,7 @@ UNITS = [
     ("gemm_dw.cu", []),
     ("optim.cu", []),
     ("camera.cu", ["-fmad=false"]),
+    ("correspondence.cu", ["-fmad=false"]),
 ]
 HEADERS = [os.path.join(CSRC, "ptx.cuh"), os.path.join(ROOT, "include", "moco_flow_b200.h")]
 

@@ -52,3 +52,15 @@ def canvas_scatter(background, rays_msk, rgb, depth, opacity):
     depth_raw[foreground_mask > 0] = depth[foreground_idx]
     img_raw[foreground_mask == 0] = background[foreground_mask == 0]
     return img_raw, depth_raw
+
+
+def nearest_vertex(verts, query, trans, thickness):
+    """datasets/moco_flow_dataset.py:121-130 with knn_cuda.KNN(k=1, transpose_mode=True) restated as a brute-force
+    argmin (knn_cuda is not installed and not vendored: parity of this piece is UNPINNED; the restatement follows its
+    documented contract -- Euclidean distance and index of the nearest reference point)."""
+    d2 = ((query[:, None, :] - verts[None, :, :]) ** 2).sum(-1)
+    best, ind = d2.min(dim=1)
+    dist = best.sqrt()
+    homo = torch.cat([query, torch.ones(query.shape[0], 1)], dim=-1)
+    cano = (trans[ind] @ homo.unsqueeze(-1))[:, :3, 0]
+    return dist, ind, cano, dist < thickness

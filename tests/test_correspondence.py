@@ -1,0 +1,62 @@
+"""Nearest-vertex correspondence sampling."""
+import pytest
+import torch
+
+from oracle import camera_oracle as cam_orc
+
+
+def _case(V, N, seed):
+    gen = torch.Generator().manual_seed(seed)
+    verts = torch.randn(V, 3, generator=gen) * 0.4
+    query = torch.cat([(torch.rand(N // 2, 3, generator=gen) - 0.5) * 3.0,
+                       verts[torch.randint(V, (N - N // 2,), generator=gen)] + torch.randn(N - N // 2, 3, generator=gen) * 0.2])
+    trans = torch.eye(4).repeat(V, 1, 1)
+    trans[:, :3, :] += torch.randn(V, 3, 4, generator=gen) * 0.1
+    return verts, query, trans
+
+
+def test_oracle_nearest_vertex_properties():
+    verts, query, trans = _case(50, 40, 0)
+    dist, ind, cano, inside = cam_orc.nearest_vertex(verts, query, trans, 0.2)
+    for q in range(query.shape[0]):
+        d = (verts - query[q]).norm(dim=1)
+        assert abs(float(d.min()) - float(dist[q])) < 1e-6 and int(d.argmin()) == int(ind[q])
+    assert torch.equal(inside, dist < 0.2)
+    # a query sitting on a vertex maps with that vertex's transform
+    d0, i0, c0, _ = cam_orc.nearest_vertex(verts, verts[7:8].clone(), trans, 0.2)
+    assert int(i0) == 7 and float(d0) == 0.0
+    assert torch.allclose(c0[0], trans[7, :3, :3] @ verts[7] + trans[7, :3, 3], atol=1e-6)
+
+
+def test_cpu_inputs_raise():
+    from moco_flow_b200 import correspondence
+    with pytest.raises(RuntimeError):
+        correspondence.nearest_vertex(torch.zeros(4, 3), torch.zeros(2, 3))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("V,N", [(6890, 20000), (1000, 257), (3, 1)])
+def test_nearest_vertex_kernel(V, N):
+    from moco_flow_b200 import correspondence, _lib as L
+    dev = torch.device("cuda:0")
+    verts, query, trans = _case(V, N, V + N)
+    dist_r, ind_r, cano_r, inside_r = cam_orc.nearest_vertex(verts, query, trans, 0.2)
+    dist, ind, cano, inside = correspondence.nearest_vertex(verts.to(dev), query.to(dev), trans.to(dev), 0.2)
+    torch.cuda.synchronize()
+    assert L.device_error_flag() == 0
+    dist, ind, cano, inside = dist.cpu(), ind.cpu(), cano.cpu(), inside.cpu()
+    assert (dist - dist_r).abs().max().item() <= 1e-6
+    same = ind == ind_r
+    # a different index is only acceptable on a numerical tie of the two distances
+    if not bool(same.all()):
+        d_alt = (verts[ind[~same]] - query[~same]).norm(dim=1)
+        assert (d_alt - dist_r[~same]).abs().max().item() <= 1e-6
+    assert float(same.float().mean()) > 0.999
+    assert (cano[same] - cano_r[same]).abs().max().item() <= 1e-5
+    near_thr = (dist_r - 0.2).abs() < 1e-6
+    assert torch.equal(inside[~near_thr], inside_r[~near_thr])
+    ins, outs = correspondence.split_correspondences(query.to(dev), cano.to(dev), inside.to(dev))
+    assert ins.shape[0] + outs.shape[0] == N and ins.shape[1] == 6
+    # distances only
+    d_only, i_only, c_none, _ = correspondence.nearest_vertex(verts.to(dev), query.to(dev))
+    assert c_none is None and torch.equal(i_only.cpu(), ind) and torch.equal(d_only.cpu(), dist)
