@@ -140,3 +140,34 @@ class FusedAdam(torch.optim.Optimizer):
                     L.LAUNCHES += 1   # the step-counter tick kernel
         ops.bump_param_epoch()   # raw-pointer writes: tell the modules to re-pack their bf16 weight images
         return loss
+
+
+def get_optimizer(optimizer_config: dict, parameters):
+    """trainer/base.py:122-139: ``{'type': 'adam'|'sgd', 'lr': ..., 'weight_decay': ...[, 'momentum': ...]}``.
+    'adam' is the fused kernel above (eps 1e-8 as in the reference); 'sgd' is torch's; the reference's own RAdam /
+    Ranger classes (utils/optimizers.py) are outside the hot path and not rebuilt."""
+    kind = optimizer_config['type']
+    if kind == 'adam':
+        return FusedAdam(parameters, lr=optimizer_config['lr'], eps=1e-8, weight_decay=optimizer_config['weight_decay'])
+    if kind == 'sgd':
+        return torch.optim.SGD(parameters, lr=optimizer_config['lr'], momentum=optimizer_config['momentum'],
+                               weight_decay=optimizer_config['weight_decay'])
+    raise NotImplementedError(f"Optimizer type {kind} not implemented yet !!!")
+
+
+def get_scheduler(scheduler_config: dict, optimizer, world_size: int = 1):
+    """trainer/base.py:141-160, including the division of the step milestones by the world size (:145-146)."""
+    from torch.optim import lr_scheduler
+    kind = scheduler_config['type']
+    if kind == 'steplr':
+        return lr_scheduler.MultiStepLR(optimizer,
+                                        milestones=[int(step // world_size) for step in scheduler_config['decay_step']],
+                                        gamma=scheduler_config['decay_gamma'])
+    if kind == 'explr':
+        return lr_scheduler.ExponentialLR(optimizer, scheduler_config['lr_decay'])
+    if kind == 'cosine':
+        return lr_scheduler.CosineAnnealingLR(optimizer, T_max=scheduler_config['num_epochs'], eta_min=1e-8)
+    if kind == 'poly':
+        return lr_scheduler.LambdaLR(
+            optimizer, lambda epoch: (1 - epoch / scheduler_config['num_epochs']) ** scheduler_config['poly_exp'])
+    raise NotImplementedError('Scheduler type {} not implemented yet !!!'.format(kind))

@@ -127,3 +127,29 @@ def test_fused_adam_update_reaches_the_packed_weights():
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(frozen, flat.param_buffer) and not torch.equal(before, frozen)
+
+
+def test_reference_optimizer_and_scheduler_factories():
+    """trainer/base.py:122-160: config dictionaries -> optimizer / scheduler, milestones divided by the world size."""
+    from moco_flow_b200.optim import get_optimizer, get_scheduler
+    nets = _nets()
+    params = [p for n in nets for p in n.parameters()]
+    opt = get_optimizer({'type': 'adam', 'lr': 1e-4, 'weight_decay': 0}, params)
+    assert isinstance(opt, FusedAdam) and opt.defaults['eps'] == 1e-8 and opt.defaults['lr'] == 1e-4
+    sgd = get_optimizer({'type': 'sgd', 'lr': 0.1, 'momentum': 0.9, 'weight_decay': 0.0}, params)
+    assert isinstance(sgd, torch.optim.SGD)
+    with pytest.raises(NotImplementedError):
+        get_optimizer({'type': 'ranger', 'lr': 1e-3, 'weight_decay': 0}, params)
+    sch = get_scheduler({'type': 'steplr', 'decay_step': [40, 80], 'decay_gamma': 0.5}, sgd, world_size=8)
+    assert sorted(sch.milestones) == [5, 10]
+    lrs = []
+    for _ in range(12):
+        lrs.append(sgd.param_groups[0]['lr'])
+        sgd.step()
+        sch.step()
+    assert lrs[4] == 0.1 and abs(lrs[5] - 0.05) < 1e-12 and abs(lrs[10] - 0.025) < 1e-12
+    for cfg in ({'type': 'explr', 'lr_decay': 0.9}, {'type': 'cosine', 'num_epochs': 10},
+                {'type': 'poly', 'num_epochs': 10, 'poly_exp': 2.0}):
+        assert get_scheduler(cfg, get_optimizer({'type': 'sgd', 'lr': 0.1, 'momentum': 0.0, 'weight_decay': 0.0}, params))
+    with pytest.raises(NotImplementedError):
+        get_scheduler({'type': 'nope'}, sgd)
