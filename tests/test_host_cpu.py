@@ -143,3 +143,17 @@ def test_plans_carry_their_program_family():
     assert int(of.rounds["epi"][-1]) == L.EPI_NOF_HEAD
     names = [f[0] for f in L.ChainParams._fields_]
     assert names[-2:] == ["cta_pair", "program_kind"]
+
+
+def test_bench_reference_arm_contract():
+    """``bench.py --impl reference`` (the CPU oracle port; the one place outside tests/ that may execute oracle/) prints
+    one JSON line with the contract's keys, on a tiny bounded sample here."""
+    import json
+    import sys
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                                   "--warmup", "0", "--cpu-rays", "16"], stderr=subprocess.DEVNULL, timeout=600)
+    line = json.loads(out.decode().strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("train rays/s") and line["value"] > 0 and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
