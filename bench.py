@@ -383,13 +383,7 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
         "scaling": "strong" if args.workload == "frame" else "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": ("MoCo-Flow training step fwd+bwd (BASELINE configs[2]): 4096 rays/GPU, 64+64 samples, "
-                                "bw/fw NoF chains (local+global), random-init c2f.yaml shapes, Adam step, "
-                                "ray-sharded DP + flat-gradient NCCL all-reduce") if train else
-                               ("full-frame inference render (BASELINE configs[3] shape): 540x540 rays per step "
-                                "sharded over the GPUs, 64+64 samples, test_time; ms_per_step = ms/frame")
-                               if args.workload == "frame" else
-                               ("full MoCo-Flow ray render (BASELINE configs[1]): 4096 rays, 64+64 samples, test_time"),
+        "config": {"workload": workload_text(args.workload),
                    "rays_per_gpu": R, "n_coarse": N_COARSE, "n_fine": N_FINE,
                    "l2": ("flushed: a 256 MB buffer is written between timed steps (outside the per-step events)"
                           if args.workload == "render" else
@@ -473,6 +467,18 @@ def cpu_baseline(workload: str, sample_rays: int, steps: int, warmup: int):
                       f"port (oracle/moco_oracle.py, torch fp32 eager, all host threads)"}
 
 
+def workload_text(workload: str) -> str:
+    """The workload description both arms put into ``config`` (same text, so the two JSON lines name the same job)."""
+    if workload == "train":
+        return ("MoCo-Flow training step fwd+bwd (BASELINE configs[2]): 4096 rays/GPU, 64+64 samples, "
+                "bw/fw NoF chains (local+global), random-init c2f.yaml shapes, Adam step, "
+                "ray-sharded DP + flat-gradient NCCL all-reduce")
+    if workload == "frame":
+        return ("full-frame inference render (BASELINE configs[3] shape): 540x540 rays per step "
+                "sharded over the GPUs, 64+64 samples, test_time; ms_per_step = ms/frame")
+    return "full MoCo-Flow ray render (BASELINE configs[1]): 4096 rays, 64+64 samples, test_time"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -497,8 +503,9 @@ def run_reference(args):
         "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "same workload as the default arm, CPU oracle port of the reference", "rays_per_step": n,
-                   "n_coarse": N_COARSE, "n_fine": N_FINE},
+        "config": {"workload": workload_text(args.workload), "n_coarse": N_COARSE, "n_fine": N_FINE,
+                   "implementation": "CPU oracle port of the reference (oracle/moco_oracle.py, torch fp32 eager)",
+                   "rays_per_step": n},
         "cpu_baseline": {"value": val, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
