@@ -124,6 +124,66 @@ def build_models(dev, seed: int = 0):
     return nerfs, nofs, nerf_embs, nof_embs
 
 
+def self_check(workload, dev, nerfs, nofs, nerf_embs, nof_embs, n_rays: int = 256):
+    """The timed computation checked against the CPU oracle on a slice of the workload (same weights, same rays, same
+    injected random draws): returns the error figures that go into the JSON line; raises if they are out of bounds --
+    a throughput number of a wrong computation is not a result."""
+    import moco_flow_b200 as mf
+    from oracle import moco_oracle as orc
+    rays, bg, tgt = synth_batch(n_rays, seed=1)
+    dr = orc.make_draws(n_rays, N_COARSE, N_FINE, seed=2)
+    draws = mf.Draws(*(t.to(dev) for t in (dr.perturb, dr.noise_coarse, dr.u, dr.noise_fine)))
+    pes = orc.C2F_PE
+    o_nerfs = [orc.NeRFBundle(orc.C2F_NERF, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}) for m in nerfs]
+    o_nofs = [orc.NoFBundle(orc.C2F_NOF, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}) for m in nofs]
+    train = workload == "train"
+    kw = dict(N_samples=N_COARSE, N_importance=N_FINE, perturb=1.0, noise_std=0.0)
+    if train:
+        kw.update(chain_local=True, chain_global=True)
+    else:
+        kw.update(test_time=True)
+    with torch.no_grad():
+        res = mf.render_rays(rays.to(dev), bg.to(dev), nerf_embs, nerfs, nof_embeddings=nof_embs, nof_models=nofs,
+                             draws=draws, fused_residual_mean=True, **kw)
+        res = {k: v.cpu() for k, v in res.items()}
+        out = {"rays": n_rays, "against": "oracle/moco_oracle.py on the host (fp32 reference algorithm, and the same with "
+                                          "bf16 tensor-core emulation)"}
+        refs = {}
+        for mode in ("fp32", "bf16_emulated"):
+            orc.EMULATE_BF16 = mode != "fp32"
+            try:
+                refs[mode] = orc.render_rays(rays, bg, [pes["nerf_xyz"], pes["nerf_ind"], None], o_nerfs,
+                                             [pes["nof_xyz"], pes["nof_ind"]], o_nofs, draws=dr, **kw)
+            finally:
+                orc.EMULATE_BF16 = False
+    for key in ("rgb_fine", "depth_fine", "opacity_fine"):
+        for mode, ref in refs.items():
+            out[f"{key}_max_abs_vs_{mode}"] = float((res[key] - ref[key]).abs().max())
+    if train:
+        def objective(r, means):
+            loss = ((r["rgb_coarse"] - tgt) ** 2).mean() + ((r["rgb_fine"] - tgt) ** 2).mean()
+            for k in ("nof_local_disp", "nof_global_disp"):
+                loss = loss + 0.2 * (means(r[k + "_coarse"]) + means(r[k + "_fine"]))
+            return float(loss)
+        out["loss"] = objective(res, lambda t: t.mean())
+        for mode, ref in refs.items():
+            out[f"loss_{mode}"] = objective(ref, lambda t: t.mean())
+        if abs(out["loss"] - out["loss_bf16_emulated"]) > 2e-3 * max(1.0, abs(out["loss_bf16_emulated"])):
+            raise SystemExit(f"bench self-check failed: loss {out}")
+    # Random-init volumes are semi-transparent up to the far plane, where the reference's last sample (delta = 1e10)
+    # turns alpha into the step function [sigma_last > 0]: a ray whose sigma_last is within bf16 rounding of zero may
+    # legitimately flip, so the bound is on the fraction of rays, and the max is reported.
+    bad = (res["rgb_fine"] - refs["bf16_emulated"]["rgb_fine"]).abs().amax(dim=1) > 1e-3
+    out["rgb_fine_rays_over_1e-3_vs_bf16_emulated"] = int(bad.sum())
+    if float(bad.float().mean()) > 0.01:
+        raise SystemExit(f"bench self-check failed: {out}")
+    from moco_flow_b200 import _lib as L
+    flag = L.device_error_flag()
+    if flag:
+        raise SystemExit(f"bench self-check: device error flag {flag:#x}")
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     import moco_flow_b200 as mf
@@ -144,6 +204,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
+        dp.enable_global_residual_means()   # masked flow-residual means over the rays of all ranks
     L.lib()
     nerfs, nofs, nerf_embs, nof_embs = build_models(dev)
     dp.broadcast_parameters(nerfs + nofs)
@@ -192,13 +253,18 @@ def run_ours(args):
             sys.stderr.flush()
 
     dbg("warm-up done")
+    parity = None
+    if rank == 0 and not args.no_self_check and args.workload in ("train", "render"):
+        parity = self_check(args.workload, dev, nerfs, nofs, nerf_embs, nof_embs)
+        dbg(f"self-check: {parity}")
     eager_step = step
     graphed = False
     if not args.no_graph:
         gstep = None
         try:
             from moco_flow_b200.graph import CudaGraphStep
-            gstep = CudaGraphStep(eager_step, [rays_d, bg_d, tgt_d], warmup=2)
+            gstep = CudaGraphStep(eager_step, [rays_d, bg_d, tgt_d], warmup=2,
+                                  refresh=[e for e in nerf_embs + nof_embs if e is not None] + ([opt] if opt else []))
         except Exception as exc:  # report, then measure the eager path
             sys.stderr.write(f"[bench rank {rank}] CUDA graph capture failed ({exc!r}); timing the eager step\n")
             gstep = None
@@ -268,6 +334,7 @@ def run_ours(args):
 
     ms_e2e = timed_steps(e2e_step)
     dbg("e2e timing done")
+    mf.check_device()   # a kernel that flagged a device-side error anywhere above fails the run
 
     # ---- frame workload only: pose -> device ray generation -> render -> canvas scatter -> image on the host ----
     ms_frame = None
@@ -394,6 +461,7 @@ def run_ours(args):
         "e2e": {"value": round(total_rays / (ms_e2e * 1e-3), 1), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": launches,
+        "parity": parity,
         "clocks": clk,
         "roofline": roofline,
         "roofline_mlp": mlp,
@@ -525,6 +593,7 @@ def main():
                          "(configs[3] shape) per step, rays sharded over the GPUs")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-self-check", action="store_true", help="skip the oracle comparison of the timed computation")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

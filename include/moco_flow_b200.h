@@ -51,10 +51,13 @@ int mcf_ray_points(const float* rays, int ray_stride, const float* z, int n_rays
                    cudaStream_t stream);
 
 /* ---- positional encoding (standalone Embedding.forward), models/embedding.py:42-46 ---------- */
+/* table_dev (may be NULL): device [2*MCF_MAX_FREQS] floats {freq[], weight[]} that override the host arrays --
+ * the form to use under CUDA-graph capture when Embedding.weights changes between replays. */
 int mcf_pe_fwd(const float* x, long long n_rows, int in_channels, int n_freqs, const float* freqs_host,
-               const float* weights_host, float* out, int out_stride, cudaStream_t stream);
+               const float* weights_host, const float* table_dev, float* out, int out_stride, cudaStream_t stream);
 int mcf_pe_bwd(const float* x, const float* dy, long long n_rows, int in_channels, int n_freqs,
-               const float* freqs_host, const float* weights_host, int dy_stride, float* dx, cudaStream_t stream);
+               const float* freqs_host, const float* weights_host, const float* table_dev, int dy_stride, float* dx,
+               cudaStream_t stream);
 
 /* out[r][n] = bias[n] + sum_j W[n][col_off+j] * feat[r][j]: exact fp32 fold of the per-ray constant
  * input columns (replaces the repeat_interleave+cat of models/rendering.py:73-75,133-142). */
@@ -85,12 +88,19 @@ int mcf_sample_pdf(const float* bins, int bins_stride, int bins_are_z, const flo
                    float* cdf_out, float* z_merged, cudaStream_t stream);
 
 /* ---- flow-consistency residual, models/rendering.py:304-314,363-373 ------------------------- */
-/* resid[m] = mean_3 |a-b| ; stats = {masked sum, masked count, total sum} (3 doubles);
- * mean_out[0] = mean of resid over alphas>=thresh (over everything if the mask is empty). */
+/* resid[m] = mean_3 |a-b| ; stats = {masked sum, masked count, total sum, total count} (4 doubles, zeroed by the
+ * call); mean_out[0] = mean of resid over alphas>=thresh (over everything if the mask is empty), or NULL to leave
+ * the mean to mcf_masked_l1_finalize -- the data-parallel path all-reduces the stats of all ranks in between so that
+ * the mean is the one over the whole (global) ray batch, as the reference's single-process step computes it
+ * (models/rendering.py:306-311 + trainer/trainer_moco_flow.py:319-327). */
 int mcf_masked_l1_fwd(const float* a, const float* b, const float* alphas, float thresh, long long n_points,
                       float* resid, double* stats, float* mean_out, cudaStream_t stream);
+int mcf_masked_l1_finalize(const double* stats, float* mean_out, cudaStream_t stream);
+/* g_resid: per-sample upstream gradient (dynamic-length compat path), or g_mean + stats: gradient of the masked
+ * mean; grad_mul scales it (world size under data parallelism: ranks' gradients are averaged afterwards). */
 int mcf_masked_l1_bwd(const float* a, const float* b, const float* alphas, float thresh, long long n_points,
-                      const float* g_resid, const float* g_mean, const double* stats, float* d_b, cudaStream_t stream);
+                      const float* g_resid, const float* g_mean, const double* stats, float grad_mul, float* d_b,
+                      cudaStream_t stream);
 
 /* ---- fused MLP chains on tcgen05/TMEM: models/nerf.py:61-102, models/nof.py:55-85 ----------- */
 /* Weights are re-packed from the fp32 nn.Linear tensors into bf16 128B-swizzled UMMA operand images
@@ -209,6 +219,11 @@ typedef struct {
   /* 0: NeRF program (sigma / rgb heads), 1: NoF program (flow head).  Selects a kernel instantiation that carries only
    * that family's prologues and epilogues; a program of the other family fails with the device error flag. */
   int32_t program_kind;
+  /* optional device copy of the encoder tables, [2*MCF_MAX_FREQS] floats = {freq[], weight[]}: when non-NULL it
+   * replaces pe_freq / pe_weight above.  The reference re-assigns Embedding.weights every step of its coarse-to-fine
+   * schedule (trainer/trainer_moco_flow.py:280-305); values passed by pointer stay current when the launch is
+   * replayed from a captured CUDA graph, values passed in this struct are frozen at capture. */
+  const float* pe_table;
 } mcf_chain_params_t;
 
 int mcf_chain_launch(const mcf_chain_params_t* params_host, cudaStream_t stream);

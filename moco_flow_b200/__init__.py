@@ -11,9 +11,10 @@ from .nerf import NeRF
 from .nof import NoF
 from .losses import MSELoss
 from .rendering import Draws, nerf_inference, nof_inference, render_rays, sample_pdf
+from .ops import check_device
 
 __all__ = ["Embedding", "NeRF", "NoF", "MSELoss", "Draws", "get_model", "get_loss", "render_rays",
-           "nerf_inference", "nof_inference", "sample_pdf"]
+           "nerf_inference", "nof_inference", "sample_pdf", "check_device"]
 
 
 def get_model(model_config):

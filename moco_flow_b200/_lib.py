@@ -56,7 +56,7 @@ class ChainParams(C.Structure):
         ("fwd_mask_tile_words", _i64), ("fwd_x0_off", _u32), ("fwd_he_off", _u32),
         ("d_xyz", _vp), ("d_head", _vp), ("rayfeat", _vp), ("rayfeat_stride", _i32), ("rayfeat_dim", _i32),
         ("extra_save_off", _u32), ("dhead_save_off", _u32), ("max_ctas", _i32),
-        ("timing", _vp), ("cta_pair", _i32), ("program_kind", _i32),
+        ("timing", _vp), ("cta_pair", _i32), ("program_kind", _i32), ("pe_table", _vp),
     ]
 
 
@@ -72,7 +72,7 @@ class DwParams(C.Structure):
 EXPORTS = [
     "mcf_abi_version", "mcf_device_error_flag", "mcf_coarse_samples", "mcf_ray_points", "mcf_pe_fwd", "mcf_pe_bwd",
     "mcf_ray_bias", "mcf_composite_fwd", "mcf_composite_bwd", "mcf_sample_pdf", "mcf_masked_l1_fwd",
-    "mcf_masked_l1_bwd", "mcf_pack", "mcf_chain_launch", "mcf_dw_gemm", "mcf_dw_gemm_batch", "mcf_unpack",
+    "mcf_masked_l1_finalize", "mcf_masked_l1_bwd", "mcf_pack", "mcf_chain_launch", "mcf_dw_gemm", "mcf_dw_gemm_batch", "mcf_unpack",
     "mcf_unpack_accumulate", "mcf_colsum", "mcf_adam_step", "mcf_make_rays", "mcf_canvas_scatter", "mcf_nearest_vertex",
 ]
 

@@ -76,8 +76,7 @@ def nof_forward_launch(model, xyz, pe, dense, ray_feat, rows_per_ray: int, train
                        model.in_channels_xyz)
     E, cx = model.extra_feat_dim, model.in_channels_xyz
     if E > 0:
-        if ray_feat is None or ray_feat.shape[0] != R:
-            raise ValueError("ray_feat with one row per ray is required")
+        check_nof_ray_feat(model, ray_feat, R)
         for k, i in enumerate(P.folded_layers(model.D, tuple(model.skips))):
             lin = getattr(model, f"nof_encoding_{i+1}")[0]
             rb = fold_bias(lin.weight, cx, lin.bias, ray_feat[:, :E])
@@ -91,6 +90,16 @@ def nof_forward_launch(model, xyz, pe, dense, ray_feat, rows_per_ray: int, train
         cp.head_save = head_save.data_ptr()
     ops.launch_chain(cp, "nof_fwd", ops.linear_flops(model))
     return out, keep, head_save
+
+
+def check_nof_ray_feat(model, ray_feat, n_rays: int) -> None:
+    """The reference concatenates the index embedding without padding (models/rendering.py:71-74), so a width other than
+    ``extra_feat_dim`` fails in its first Linear; a silent zero-pad / truncation here would hide that."""
+    if ray_feat is None or ray_feat.shape[0] != n_rays:
+        raise ValueError("ray_feat with one row per ray is required")
+    if ray_feat.shape[1] != model.extra_feat_dim:
+        raise RuntimeError(f"NoF expects a {model.extra_feat_dim}-wide per-ray feature, got {ray_feat.shape[1]} "
+                           "(mat1 and mat2 shapes cannot be multiplied in the reference)")
 
 
 def nof_apply(model, xyz, pe, dense, ray_feat, rows_per_ray):

@@ -196,7 +196,7 @@ class _NeRFFn(torch.autograd.Function):
         if need_dx:
             d_xyz = torch.empty(M, 3, device=dev)
             cp.d_xyz = d_xyz.data_ptr()
-            ops.set_pe(cp, ctx.pe.frequencies(), ctx.pe.multipliers(), model.in_channels_xyz)
+            ops.set_pe(cp, ctx.pe, model.in_channels_xyz, dev)
         first = 2.0 * model.in_channels_xyz * model.W * (1 + len([s for s in model.skips if s > 0]))
         ops.launch_chain(cp, "nerf_bwd_dx", ops.linear_flops(model) - (0.0 if need_dx else first))
         needs = list(ctx.needs_input_grad[7:])
@@ -246,6 +246,8 @@ class _NoFFn(torch.autograd.Function):
         keep = setup_input(cp, xyz_c, pe, None if dense is None else dense.detach(), model.in_channels_xyz)
         E, cx = model.extra_feat_dim, model.in_channels_xyz
         if E > 0:
+            from .autograd_mlp import check_nof_ray_feat
+            check_nof_ray_feat(model, ray_feat, R)
             rf = ray_feat[:, :E].detach()
             if rf.stride(-1) != 1:
                 rf = rf.contiguous()
@@ -311,7 +313,7 @@ class _NoFFn(torch.autograd.Function):
         if need_dx:
             d_xyz = torch.empty(M, 3, device=dev)
             cp.d_xyz = d_xyz.data_ptr()
-            ops.set_pe(cp, ctx.pe.frequencies(), ctx.pe.multipliers(), model.in_channels_xyz)
+            ops.set_pe(cp, ctx.pe, model.in_channels_xyz, dev)
         first = 2.0 * model.in_channels_xyz * model.W * (1 + len([s for s in model.skips if s > 0]))
         ops.launch_chain(cp, "nof_bwd_dx", ops.linear_flops(model) - (0.0 if need_dx else first))
         needs = list(ctx.needs_input_grad[7:])

@@ -29,7 +29,7 @@
 namespace mcf {
 
 constexpr int kThreads = 384;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 4;
 constexpr int kProducers = 1;  // producer warps (0, then 2, 3).  Three were measured against one in both ring modes: no gain
 constexpr uint32_t kBlk = MCF_BLOCK_BYTES;
 constexpr int kMaxChunks = 128;
@@ -47,6 +47,8 @@ struct Tables {
   uint64_t acc_full[2];
   uint32_t tmem_base;
   uint32_t pad[3];
+  float pe_freq[12];    // encoder tables: from the launch parameters, or from p.pe_table (device) when given
+  float pe_weight[12];
 };
 
 template <int W>
@@ -265,6 +267,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     const uint32_t* src_r = reinterpret_cast<const uint32_t*>(p.rounds);
     uint32_t* dst_r = reinterpret_cast<uint32_t*>(tab.rounds);
     for (int i = threadIdx.x; i < p.n_rounds * 8; i += kThreads) dst_r[i] = src_r[i];
+    if (threadIdx.x < 10) {
+      const int k = threadIdx.x;
+      tab.pe_freq[k] = p.pe_table ? p.pe_table[k] : p.pe_freq[k];
+      tab.pe_weight[k] = p.pe_table ? p.pe_table[MCF_MAX_FREQS + k] : p.pe_weight[k];
+    }
     uint4* x0z = reinterpret_cast<uint4*>(smem + L::off_x0);
     for (int i = threadIdx.x; i < (int)(2 * kBlk / 16); i += kThreads) x0z[i] = make_uint4(0, 0, 0, 0);
   }
@@ -508,10 +515,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
           if (k < p.pe_n_freqs) {
-            const float f = p.pe_freq[k], w = p.pe_weight[k];
+            const float f = tab.pe_freq[k], w = tab.pe_weight[k];
             // full-range sincosf at every 4th octave; in between sin/cos(2a) from sin/cos(a) (<= 3 doublings,
             // error <= ~8 ulp, far below the bf16 rounding of the operand); non-octave tables stay exact
-            const bool exact = (k & 3) == 0 || f != 2.0f * p.pe_freq[k > 0 ? k - 1 : 0];
+            const bool exact = (k & 3) == 0 || f != 2.0f * tab.pe_freq[k > 0 ? k - 1 : 0];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               if (exact) {
@@ -827,7 +834,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
 #pragma unroll
           for (int k = 0; k < 10; ++k) {
             if (k < p.pe_n_freqs) {
-              const float f = p.pe_freq[k];
+              const float f = tab.pe_freq[k];
 #pragma unroll
               for (int c = 0; c < 3; ++c) {
                 const int is = 3 + 6 * k + c, ic = is + 3;

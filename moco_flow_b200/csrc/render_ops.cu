@@ -79,8 +79,9 @@ struct PEArgs {
   float weight[MCF_MAX_FREQS];
 };
 
-__global__ void k_pe_fwd(const float* __restrict__ x, long long B, int C, PEArgs pe, int out_stride,
-                         float* __restrict__ out) {
+// tab (optional): device {freq[MCF_MAX_FREQS], weight[MCF_MAX_FREQS]} overriding the by-value tables
+__global__ void k_pe_fwd(const float* __restrict__ x, long long B, int C, PEArgs pe, const float* __restrict__ tab,
+                         int out_stride, float* __restrict__ out) {
   int OC = C * (2 * pe.n_freqs + 1);
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= B * OC) return;
@@ -92,15 +93,15 @@ __global__ void k_pe_fwd(const float* __restrict__ x, long long B, int C, PEArgs
   } else {
     int q = (oc - C) / C, c = (oc - C) - q * C;
     int k = q >> 1;
-    float arg = pe.freq[k] * x[m * C + c];
-    v = pe.weight[k] * ((q & 1) ? cosf(arg) : sinf(arg));
+    float arg = (tab ? tab[k] : pe.freq[k]) * x[m * C + c];
+    v = (tab ? tab[MCF_MAX_FREQS + k] : pe.weight[k]) * ((q & 1) ? cosf(arg) : sinf(arg));
   }
   out[m * out_stride + oc] = v;
 }
 
 // dx[m,c] = dy[m,c] + sum_k w_k f_k (cos(f_k x) dy_sin - sin(f_k x) dy_cos)
 __global__ void k_pe_bwd(const float* __restrict__ x, const float* __restrict__ dy, long long B, int C, PEArgs pe,
-                         int dy_stride, float* __restrict__ dx) {
+                         const float* __restrict__ tab, int dy_stride, float* __restrict__ dx) {
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= B * C) return;
   long long m = idx / C;
@@ -110,8 +111,9 @@ __global__ void k_pe_bwd(const float* __restrict__ x, const float* __restrict__ 
   float acc = g[c];
   for (int k = 0; k < pe.n_freqs; ++k) {
     float s, co;
-    sincosf(pe.freq[k] * xv, &s, &co);
-    float wf = pe.weight[k] * pe.freq[k];
+    const float fk = tab ? tab[k] : pe.freq[k];
+    sincosf(fk * xv, &s, &co);
+    float wf = (tab ? tab[MCF_MAX_FREQS + k] : pe.weight[k]) * fk;
     acc += wf * (co * g[C + (2 * k) * C + c] - s * g[C + (2 * k + 1) * C + c]);
   }
   dx[idx] = acc;
@@ -458,7 +460,7 @@ k_sample_pdf(const float* __restrict__ bins, int bins_stride, int bins_are_z, co
 // -------------------------------------------------------------------------------------------------
 // masked flow-consistency residual
 // -------------------------------------------------------------------------------------------------
-// stats: [0] masked sum (double), [1] masked count (double), [2] total sum (double)
+// stats: [0] masked sum, [1] masked count, [2] total sum, [3] total count (doubles)
 __global__ void k_masked_l1_fwd(const float* __restrict__ a, const float* __restrict__ b,
                                 const float* __restrict__ alphas, float thresh, long long M,
                                 float* __restrict__ resid, double* __restrict__ stats) {
@@ -494,14 +496,17 @@ __global__ void k_masked_l1_fwd(const float* __restrict__ a, const float* __rest
       atomicAdd(&stats[0], ms);
       atomicAdd(&stats[1], mc);
       atomicAdd(&stats[2], ts);
+      long long first = blockIdx.x * (long long)blockDim.x;
+      long long n_here = M - first < (long long)blockDim.x ? M - first : (long long)blockDim.x;
+      atomicAdd(&stats[3], (double)(n_here > 0 ? n_here : 0));
     }
   }
 }
 
 // mean over the selected samples (all samples if none is selected): rendering.py:306-311 + torch.mean
-__global__ void k_masked_l1_finalize(const double* __restrict__ stats, long long M, float* __restrict__ out) {
+__global__ void k_masked_l1_finalize(const double* __restrict__ stats, float* __restrict__ out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double v = stats[1] > 0.0 ? stats[0] / stats[1] : stats[2] / (double)M;
+    double v = stats[1] > 0.0 ? stats[0] / stats[1] : stats[2] / stats[3];
     out[0] = static_cast<float>(v);
   }
 }
@@ -510,7 +515,7 @@ __global__ void k_masked_l1_finalize(const double* __restrict__ stats, long long
 __global__ void k_masked_l1_bwd(const float* __restrict__ a, const float* __restrict__ b,
                                 const float* __restrict__ alphas, float thresh, long long M,
                                 const float* __restrict__ g_resid, const float* __restrict__ g_mean,
-                                const double* __restrict__ stats, float* __restrict__ d_b) {
+                                const double* __restrict__ stats, float grad_mul, float* __restrict__ d_b) {
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= M) return;
   float g;
@@ -519,8 +524,8 @@ __global__ void k_masked_l1_bwd(const float* __restrict__ a, const float* __rest
   } else {
     double cnt = stats[1];
     bool sel = cnt > 0.0 ? (alphas[idx] >= thresh) : true;
-    double n = cnt > 0.0 ? cnt : (double)M;
-    g = sel ? static_cast<float>((double)g_mean[0] / n) : 0.f;
+    double n = cnt > 0.0 ? cnt : stats[3];
+    g = sel ? static_cast<float>((double)g_mean[0] * (double)grad_mul / n) : 0.f;
   }
   g = g / 3.0f;
 #pragma unroll
@@ -573,22 +578,23 @@ int mcf_ray_points(const float* rays, int ray_stride, const float* z, int n_rays
 }
 
 int mcf_pe_fwd(const float* x, long long n_rows, int in_channels, int n_freqs, const float* freqs_host,
-               const float* weights_host, float* out, int out_stride, cudaStream_t stream) {
+               const float* weights_host, const float* table_dev, float* out, int out_stride, cudaStream_t stream) {
   if (n_freqs > MCF_MAX_FREQS || n_freqs < 0) return MCF_ERR_BAD_ARG;
   if (n_rows <= 0) return 0;
   PEArgs pe = make_pe(n_freqs, freqs_host, weights_host);
   long long n = n_rows * in_channels * (2 * n_freqs + 1);
-  k_pe_fwd<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, n_rows, in_channels, pe, out_stride, out);
+  k_pe_fwd<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, n_rows, in_channels, pe, table_dev, out_stride, out);
   return check_launch();
 }
 
 int mcf_pe_bwd(const float* x, const float* dy, long long n_rows, int in_channels, int n_freqs,
-               const float* freqs_host, const float* weights_host, int dy_stride, float* dx, cudaStream_t stream) {
+               const float* freqs_host, const float* weights_host, const float* table_dev, int dy_stride, float* dx,
+               cudaStream_t stream) {
   if (n_freqs > MCF_MAX_FREQS || n_freqs < 0) return MCF_ERR_BAD_ARG;
   if (n_rows <= 0) return 0;
   PEArgs pe = make_pe(n_freqs, freqs_host, weights_host);
   long long n = n_rows * in_channels;
-  k_pe_bwd<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, dy, n_rows, in_channels, pe, dy_stride, dx);
+  k_pe_bwd<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, dy, n_rows, in_channels, pe, table_dev, dy_stride, dx);
   return check_launch();
 }
 
@@ -665,20 +671,27 @@ int mcf_masked_l1_fwd(const float* a, const float* b, const float* alphas, float
                       float* resid, double* stats, float* mean_out, cudaStream_t stream) {
   if (n_points <= 0) return 0;
   if (stats) {
-    cudaError_t e = cudaMemsetAsync(stats, 0, 3 * sizeof(double), stream);
+    cudaError_t e = cudaMemsetAsync(stats, 0, 4 * sizeof(double), stream);
     if (e != cudaSuccess) return (int)e;
   }
   k_masked_l1_fwd<<<(unsigned)((n_points + 255) / 256), 256, 0, stream>>>(a, b, alphas, thresh, n_points, resid, stats);
-  if (stats && mean_out) k_masked_l1_finalize<<<1, 32, 0, stream>>>(stats, n_points, mean_out);
+  if (stats && mean_out) k_masked_l1_finalize<<<1, 32, 0, stream>>>(stats, mean_out);
+  return check_launch();
+}
+
+int mcf_masked_l1_finalize(const double* stats, float* mean_out, cudaStream_t stream) {
+  if (!stats || !mean_out) return MCF_ERR_BAD_ARG;
+  k_masked_l1_finalize<<<1, 32, 0, stream>>>(stats, mean_out);
   return check_launch();
 }
 
 int mcf_masked_l1_bwd(const float* a, const float* b, const float* alphas, float thresh, long long n_points,
-                      const float* g_resid, const float* g_mean, const double* stats, float* d_b, cudaStream_t stream) {
+                      const float* g_resid, const float* g_mean, const double* stats, float grad_mul, float* d_b,
+                      cudaStream_t stream) {
   if (n_points <= 0) return 0;
   if (!g_resid && !(g_mean && stats)) return MCF_ERR_BAD_ARG;
   k_masked_l1_bwd<<<(unsigned)((n_points + 255) / 256), 256, 0, stream>>>(a, b, alphas, thresh, n_points, g_resid,
-                                                                         g_mean, stats, d_b);
+                                                                         g_mean, stats, grad_mul, d_b);
   return check_launch();
 }
 

@@ -15,6 +15,25 @@ import torch
 import torch.distributed as dist
 
 
+def _params_rewritten() -> None:
+    """Writes through ``p.data`` advance no version counter: tell the modules to re-pack their bf16 weight images."""
+    from . import ops
+    ops.bump_param_epoch()
+
+
+def enable_global_residual_means(group=None) -> None:
+    """From now on the fused flow-residual means of ``render_rays(fused_residual_mean=True)`` are taken over the rays of
+    ALL ranks: the (masked sum, count) pairs of a call are summed with one small all-reduce before the division, and
+    the backward scales by world/count_global, so that the rank-averaged gradients equal the gradients of the
+    single-process loss on the concatenated batch (models/rendering.py:306-314,365-373 +
+    trainer/trainer_moco_flow.py:319-327 define that global mean).  No-op without an initialised process group."""
+    from . import ops
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        ops.RESIDUAL_DP = (group, dist.get_world_size(group))
+    else:
+        ops.RESIDUAL_DP = None
+
+
 def shard_bounds(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous, balanced [begin, end) slice of ``n_items`` for ``rank`` (first ranks get the remainder)."""
     base, rem = divmod(n_items, world)
@@ -78,10 +97,23 @@ class FlatGradients:
         else:
             for p in self.params:
                 dist.broadcast(p.data, src=src, group=group)
+        _params_rewritten()
+
+    def check_views(self) -> None:
+        """Every ``.grad`` must still alias the flat buffer (an ``optimizer.zero_grad(set_to_none=True)`` or a
+        ``p.grad = None`` in between would silently exclude that parameter from the all-reduce)."""
+        off = 0
+        base = self.buffer.data_ptr()
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != base + 4 * off:
+                raise RuntimeError("a parameter's .grad no longer aliases the FlatGradients buffer (zero_grad with "
+                                   "set_to_none=True?); use FlatGradients.zero() or FusedAdam.zero_grad()")
+            off += p.numel()
 
     def allreduce_sum(self, group=None) -> float:
         """Sum over ranks; returns the factor (1/world) the caller still has to apply -- ``FusedAdam.step(grad_scale=)``
         folds it into the update instead of spending a pass over the buffer."""
+        self.check_views()
         if not (dist.is_available() and dist.is_initialized()):
             return 1.0
         world = dist.get_world_size(group)
@@ -92,6 +124,7 @@ class FlatGradients:
 
     def allreduce_mean(self, group=None) -> None:
         """Sum over ranks then divide by the world size (no-op without an initialised process group)."""
+        self.check_views()
         if not (dist.is_available() and dist.is_initialized()):
             return
         world = dist.get_world_size(group)
@@ -108,3 +141,4 @@ def broadcast_parameters(modules: Iterable[torch.nn.Module], src: int = 0, group
     for m in modules:
         for p in m.parameters():
             dist.broadcast(p.data, src=src, group=group)
+    _params_rewritten()

@@ -13,6 +13,7 @@ from typing import List, Sequence, Union
 import torch
 from torch import nn
 
+from . import _lib as L
 from . import ops
 
 
@@ -46,5 +47,40 @@ class Embedding(nn.Module):
     def multipliers(self) -> List[float]:
         return [float(w) for w in self.weights]
 
+    # -- device copy of (frequencies, weights): what the kernels read ------------------------------------
+    def device_table(self, device) -> torch.Tensor:
+        """[2*MAX_FREQS] floats {freq[], weight[]} on ``device``, brought up to date with ``self.weights``.
+
+        The kernels read the tables through this pointer, not from launch arguments, so a captured CUDA graph keeps
+        following the coarse-to-fine schedule that re-assigns ``weights`` every step
+        (trainer/trainer_moco_flow.py:280-305): call ``sync_device()`` (or pass the embeddings to
+        ``graph.CudaGraphStep(..., refresh=)``) before each replay.  While a stream is capturing, the table must
+        already be current -- a changed ``weights`` raises instead of freezing a stale copy into the graph."""
+        device = torch.device(device)
+        tables = self.__dict__.setdefault("_mcf_tables", {})
+        want = tuple(self.frequencies()) + tuple(self.multipliers())
+        ent = tables.get(device)
+        if ent is not None and ent[1] == want:
+            return ent[0]
+        if self.N_freqs > L.MAX_FREQS:
+            raise ValueError(f"at most {L.MAX_FREQS} frequencies supported")
+        if device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("Embedding.weights changed while a CUDA graph is being captured; call sync_device() first")
+        host = torch.zeros(2 * L.MAX_FREQS)
+        host[:self.N_freqs] = torch.tensor(self.frequencies())
+        host[L.MAX_FREQS:L.MAX_FREQS + self.N_freqs] = torch.tensor(self.multipliers())
+        if ent is None:
+            ent = (host.to(device), want)
+        else:
+            ent[0].copy_(host)       # same storage: pointers captured in a graph stay valid
+            ent = (ent[0], want)
+        tables[device] = ent
+        return ent[0]
+
+    def sync_device(self) -> None:
+        """Refreshes every device table from ``self.weights`` (cheap no-op when nothing changed)."""
+        for device in list(self.__dict__.get("_mcf_tables", {})):
+            self.device_table(device)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return ops.pe_forward(x, self.frequencies(), self.multipliers())
+        return ops.pe_forward(x, self.frequencies(), self.multipliers(), self.device_table(x.device) if x.is_cuda else None)

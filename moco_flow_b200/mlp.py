@@ -119,7 +119,7 @@ def setup_input(cp: L.ChainParams, xyz: Optional[torch.Tensor], pe, dense: Optio
         if pe.in_channels != 3:
             raise ValueError("the fused xyz encoder expects 3 input channels")
         cp.prologue = L.PRO_PE_XYZ
-        ops.set_pe(cp, pe.frequencies(), pe.multipliers(), cx)
+        ops.set_pe(cp, pe, cx, (xyz if xyz is not None else dense).device)
     if xyz is not None:
         cp.xyz = xyz.data_ptr()
         keep.append(xyz)

@@ -7,6 +7,7 @@ tensors -- there is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import os as _os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -14,6 +15,20 @@ import torch
 
 from . import _lib as L
 from . import plans as P
+
+
+# MCF_DEBUG=1: every render_rays call ends with a device synchronisation and a check of the kernels' error flag
+# (unknown epilogue / prologue for the launched kernel family, an expired bounded barrier wait, misaligned shared
+# memory).  Without it the flag is checked wherever the host synchronises anyway: ``check_device()``.
+DEBUG_SYNC = _os.environ.get("MCF_DEBUG", "0") == "1"
+
+
+def check_device() -> None:
+    """Synchronises and raises if any kernel of the library reported a device-side error since the last check."""
+    flag = L.device_error_flag()
+    if flag:
+        raise L.MocoFlowLibraryError(f"device error flag {flag:#010x} (0xBADExxxx unknown epilogue, 0xBADFxxxx unknown "
+                                     f"prologue, 0xDEADxxxx barrier wait expired, 0xA11Cxxxx shared-memory alignment)")
 
 
 def _need_cuda(*ts):
@@ -65,7 +80,7 @@ def ray_points(rays: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 class _PEFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, freqs, weights):
+    def forward(ctx, x, freqs, weights, table):
         x = _c(x)
         _need_cuda(x)
         B, Cin = x.shape
@@ -74,26 +89,29 @@ class _PEFn(torch.autograd.Function):
             raise ValueError(f"at most {L.MAX_FREQS} frequencies supported")
         out = torch.empty(B, Cin * (2 * nf + 1), device=x.device)
         L.check(L.lib().mcf_pe_fwd(L.ptr(x), C.c_longlong(B), C.c_int(Cin), C.c_int(nf), L.f32_array(freqs),
-                                   L.f32_array(weights), L.ptr(out), C.c_int(out.shape[1]), L.stream_ptr()),
-                "mcf_pe_fwd")
+                                   L.f32_array(weights), L.ptr(table), L.ptr(out), C.c_int(out.shape[1]),
+                                   L.stream_ptr()), "mcf_pe_fwd")
         ctx.save_for_backward(x)
-        ctx.fw = (list(freqs), list(weights))
+        ctx.fw = (list(freqs), list(weights), table)
         return out
 
     @staticmethod
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
-        freqs, weights = ctx.fw
+        freqs, weights, table = ctx.fw
         dy = _c(dy)
         dx = torch.empty_like(x)
         L.check(L.lib().mcf_pe_bwd(L.ptr(x), L.ptr(dy), C.c_longlong(x.shape[0]), C.c_int(x.shape[1]),
-                                   C.c_int(len(freqs)), L.f32_array(freqs), L.f32_array(weights),
+                                   C.c_int(len(freqs)), L.f32_array(freqs), L.f32_array(weights), L.ptr(table),
                                    C.c_int(dy.shape[1]), L.ptr(dx), L.stream_ptr()), "mcf_pe_bwd")
-        return dx, None, None
+        return dx, None, None, None
 
 
-def pe_forward(x: torch.Tensor, freqs: Sequence[float], weights: Sequence[float]) -> torch.Tensor:
-    return _PEFn.apply(x, tuple(freqs), tuple(weights))
+def pe_forward(x: torch.Tensor, freqs: Sequence[float], weights: Sequence[float],
+               table: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``table``: device {freq[], weight[]} copy (Embedding.device_table) that the kernel reads instead of the
+    by-value arrays."""
+    return _PEFn.apply(x, tuple(freqs), tuple(weights), table)
 
 
 def ray_bias(weight: torch.Tensor, col_off: int, bias: Optional[torch.Tensor], feat: torch.Tensor) -> torch.Tensor:
@@ -174,17 +192,38 @@ def composite(raw, z, dirs, noise, noise_std, background, activate_type):
 # ------------------------------------------------------------------------------------------------
 # sample_pdf (+ sort-merge)
 # ------------------------------------------------------------------------------------------------
+# How the cdf of sample_pdf is built when the caller passes weights (exactness contract):
+#   False (default) -- "reference order": the reference's own four torch ops (rendering.py:20-23) on the same device,
+#                      so the cdf -- and with it every index -- is bit-identical to the reference run on this GPU;
+#                      the kernel fuses everything after the cdf (search, gather, lerp, sort-merge).
+#   True            -- the kernel builds the cdf itself in a fixed order (fp64 total, fp64 running sum rounded per
+#                      entry); one pass less, indices can differ from torch's where u is within 1 ulp of a cdf entry.
+FUSED_CDF = _os.environ.get("MCF_FUSED_CDF", "0") == "1"
+
+
+def reference_cdf(weights: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """rendering.py:20-23, literally (same ops, same order, same device)."""
+    weights = weights + eps
+    pdf = weights / torch.sum(weights, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    return torch.cat([torch.zeros_like(cdf[:, :1]), cdf], -1)
+
+
 def sample_pdf_raw(bins: torch.Tensor, weights: Optional[torch.Tensor], u: torch.Tensor, eps: float = 1e-5,
                    bins_are_z: bool = False, w_offset: int = 0, n_bins: Optional[int] = None,
                    cdf: Optional[torch.Tensor] = None, z_coarse: Optional[torch.Tensor] = None,
-                   want_samples: bool = True, want_inds: bool = False, want_cdf: bool = False):
+                   want_samples: bool = True, want_inds: bool = False, want_cdf: bool = False,
+                   fused_cdf: Optional[bool] = None):
     """models/rendering.py:5-46 (+:326).  ``weights`` may be a wider row of which columns
     [w_offset, w_offset+n_bins) are the bin weights (the reference passes weights[:, 1:-1])."""
+    if n_bins is None:
+        n_bins = (weights.shape[1] - w_offset) if weights is not None else cdf.shape[1] - 1
+    if cdf is None and not (FUSED_CDF if fused_cdf is None else fused_cdf):
+        _need_cuda(weights)
+        cdf, weights = reference_cdf(weights[:, w_offset:w_offset + n_bins], eps), None
     bins, weights, u, cdf, z_coarse = _c(bins), _c(weights), _c(u), _c(cdf), _c(z_coarse)
     _need_cuda(bins, weights, u, cdf, z_coarse)
     R, n_imp = u.shape
-    if n_bins is None:
-        n_bins = (weights.shape[1] - w_offset) if weights is not None else cdf.shape[1] - 1
     dev = u.device
     samples = torch.empty(R, n_imp, device=dev) if want_samples else None
     inds = torch.empty(R, n_imp, device=dev, dtype=torch.int32) if want_inds else None
@@ -227,25 +266,22 @@ class _ResidualFn(torch.autograd.Function):
         d_b = torch.empty_like(b)
         L.check(L.lib().mcf_masked_l1_bwd(L.ptr(a), L.ptr(b), L.ptr(alphas), C.c_float(0.01),
                                           C.c_longlong(alphas.numel()), L.ptr(g), C.c_void_p(0), C.c_void_p(0),
-                                          L.ptr(d_b), L.stream_ptr()), "mcf_masked_l1_bwd")
+                                          C.c_float(1.0), L.ptr(d_b), L.stream_ptr()), "mcf_masked_l1_bwd")
         return None, d_b, None
 
 
 class _MaskedMeanFn(torch.autograd.Function):
     """Sync-free fused form: mean of the residual over alphas>=0.01 (all samples if none), as a (1,)
-    tensor -- torch.mean of it equals torch.mean of the reference's dynamic-length vector."""
+    tensor -- torch.mean of it equals torch.mean of the reference's dynamic-length vector.  ``stats`` holds the
+    {masked sum, masked count, total sum, total count} of the residual (already summed over the data-parallel ranks
+    when there are several); ``grad_mul`` is the world size (the ranks' gradients are averaged afterwards)."""
 
     @staticmethod
-    def forward(ctx, a, b, alphas):
-        a, b, alphas = _c(a), _c(b), _c(alphas)
-        _need_cuda(a, b, alphas)
-        M = alphas.numel()
-        stats = torch.empty(3, device=a.device, dtype=torch.float64)
+    def forward(ctx, a, b, alphas, stats, grad_mul):
         out = torch.empty(1, device=a.device)
-        L.check(L.lib().mcf_masked_l1_fwd(L.ptr(a), L.ptr(b), L.ptr(alphas), C.c_float(0.01), C.c_longlong(M),
-                                          C.c_void_p(0), L.ptr(stats), L.ptr(out), L.stream_ptr()),
-                "mcf_masked_l1_fwd")
+        L.check(L.lib().mcf_masked_l1_finalize(L.ptr(stats), L.ptr(out), L.stream_ptr()), "mcf_masked_l1_finalize")
         ctx.save_for_backward(a, b, alphas, stats)
+        ctx.grad_mul = float(grad_mul)
         return out
 
     @staticmethod
@@ -255,8 +291,46 @@ class _MaskedMeanFn(torch.autograd.Function):
         d_b = torch.empty_like(b)
         L.check(L.lib().mcf_masked_l1_bwd(L.ptr(a), L.ptr(b), L.ptr(alphas), C.c_float(0.01),
                                           C.c_longlong(alphas.numel()), C.c_void_p(0), L.ptr(g), L.ptr(stats),
-                                          L.ptr(d_b), L.stream_ptr()), "mcf_masked_l1_bwd")
-        return None, d_b, None
+                                          C.c_float(ctx.grad_mul), L.ptr(d_b), L.stream_ptr()), "mcf_masked_l1_bwd")
+        return None, d_b, None, None, None
+
+
+# Data parallelism: (process group, world size) over which the masked residual statistics are summed before the mean
+# is taken, so that every rank computes the mean over the whole ray batch of the step (set by
+# dp.enable_global_residual_means; None = this process's rays only).
+RESIDUAL_DP = None
+
+
+class ResidualMeans:
+    """The fused flow-residual means of one render_rays call: every residual's statistics go into one row of a
+    [n][4] fp64 tensor, ONE all-reduce sums the rows over the data-parallel ranks, then each mean is finalised."""
+
+    def __init__(self, device, capacity: int = 4):
+        self.stats = torch.zeros(capacity, 4, dtype=torch.float64, device=device)
+        self.pending = []
+
+    def add(self, key: str, x_obs, x_rec, alphas) -> None:
+        a, b, alphas = _c(x_obs.detach()), _c(x_rec), _c(alphas.detach())
+        _need_cuda(a, b, alphas)
+        row = self.stats[len(self.pending)]
+        L.check(L.lib().mcf_masked_l1_fwd(L.ptr(a), L.ptr(b.detach()), L.ptr(alphas), C.c_float(0.01),
+                                          C.c_longlong(alphas.numel()), C.c_void_p(0), L.ptr(row), C.c_void_p(0),
+                                          L.stream_ptr()), "mcf_masked_l1_fwd")
+        self.pending.append((key, a, b, alphas, row))
+
+    def finish(self, result: dict) -> None:
+        if not self.pending:
+            return
+        mul = 1.0
+        if RESIDUAL_DP is not None:
+            import torch.distributed as dist
+            group, world = RESIDUAL_DP
+            if world > 1:
+                dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=group)
+                mul = float(world)
+        for key, a, b, alphas, row in self.pending:
+            result[key] = _MaskedMeanFn.apply(a, b, alphas, row, mul)
+        self.pending = []
 
 
 def flow_residual(x_obs, x_rec, alphas, fused_mean: bool = False):
@@ -264,7 +338,11 @@ def flow_residual(x_obs, x_rec, alphas, fused_mean: bool = False):
     vector (one host sync, like the reference's torch.any); ``True`` returns the (1,) masked mean."""
     x_obs = x_obs.detach()
     if fused_mean:
-        return _MaskedMeanFn.apply(x_obs, x_rec, alphas)
+        rm = ResidualMeans(x_obs.device, 1)
+        rm.add("r", x_obs, x_rec, alphas)
+        out = {}
+        rm.finish(out)
+        return out["r"]
     resid = _ResidualFn.apply(x_obs, x_rec, alphas)
     mask = alphas >= 0.01
     if not bool(torch.any(mask)):
@@ -275,7 +353,6 @@ def flow_residual(x_obs, x_rec, alphas, fused_mean: bool = False):
 # ------------------------------------------------------------------------------------------------
 # fused MLP chains
 # ------------------------------------------------------------------------------------------------
-import os as _os
 # Width-256 chains run on CTA pairs (tcgen05 cta_group::2, see mcf_chain_params_t.cta_pair): bit-identical to the
 # one-CTA-per-tile-pair path (tests/test_gpu_chain.py::test_nerf_cta_pair_matches_single), 8-9 % faster on the training
 # chains, equal on inference.  MCF_CTA_PAIR=0 selects the single-CTA path.
@@ -336,12 +413,16 @@ def chain_params(pp: PackedPlan, n_rows: int, rows_per_ray: int, n_rays: int) ->
     return cp
 
 
-def set_pe(cp: L.ChainParams, freqs: Sequence[float], weights: Sequence[float], pad_to: int) -> None:
+def set_pe(cp: L.ChainParams, pe, pad_to: int, device) -> None:
+    """Encoder tables of a chain launch: by value (plain C-ABI callers) and as the Embedding's device table, which
+    is what the kernel reads (stays current under CUDA-graph replay, see Embedding.device_table)."""
+    freqs, weights = pe.frequencies(), pe.multipliers()
     if len(freqs) > 10:
         raise ValueError("the fused xyz encoder supports at most 10 frequencies (63 channels)")
     cp.pe_n_freqs, cp.pe_pad_to = len(freqs), pad_to
     for i, (f, w) in enumerate(zip(freqs, weights)):
         cp.pe_freq[i], cp.pe_weight[i] = float(f), float(w)
+    cp.pe_table = pe.device_table(device).data_ptr()
 
 
 TIMING = None  # when a dict: tag -> list of [n_ctas][16] in-kernel cycle-counter tensors (scripts/chain_timing.py)

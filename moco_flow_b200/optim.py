@@ -105,6 +105,19 @@ class FusedAdam(torch.optim.Optimizer):
         super().load_state_dict(state_dict)
         self._plans.clear()
 
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """Zeroes the gradients IN PLACE by default (torch's default drops them).  The reference calls
+        ``optimizer.zero_grad()`` every step (trainer/base.py:188-190); with ``dp.FlatGradients`` every ``.grad`` is a
+        view of the flat all-reduce buffer, and dropping the views would make the backward allocate fresh tensors that
+        the all-reduce never sees.  ``set_to_none=True`` is refused for such views."""
+        if set_to_none:
+            for group in self.param_groups:
+                for p in group["params"]:
+                    if p.grad is not None and p.grad._base is not None:
+                        raise RuntimeError("FusedAdam.zero_grad(set_to_none=True) would detach gradients that are views "
+                                           "of a flat buffer (dp.FlatGradients); use zero_grad() / FlatGradients.zero()")
+        super().zero_grad(set_to_none=set_to_none)
+
     def sync_lr(self) -> None:
         """Copies every group's ``lr`` to its device scalar (call after a scheduler step, outside graph capture)."""
         for gi, group in enumerate(self.param_groups):

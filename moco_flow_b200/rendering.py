@@ -92,9 +92,12 @@ def render_rays(rays, background, nerf_embeddings, nerf_models, nof_embeddings=N
     """rendering.py:195-375."""
     from .mlp import call_memo
     with call_memo():
-        return _render_rays(rays, background, nerf_embeddings, nerf_models, nof_embeddings, nof_models, chain_local,
-                            chain_global, N_samples, N_importance, use_disp, perturb, noise_std, nerf_activate_type,
-                            test_time, draws, fused_residual_mean)
+        result = _render_rays(rays, background, nerf_embeddings, nerf_models, nof_embeddings, nof_models, chain_local,
+                              chain_global, N_samples, N_importance, use_disp, perturb, noise_std, nerf_activate_type,
+                              test_time, draws, fused_residual_mean)
+    if ops.DEBUG_SYNC and not torch.cuda.is_current_stream_capturing():
+        ops.check_device()
+    return result
 
 
 def _render_rays(rays, background, nerf_embeddings, nerf_models, nof_embeddings, nof_models, chain_local, chain_global,
@@ -128,11 +131,18 @@ def _render_rays(rays, background, nerf_embeddings, nerf_models, nof_embeddings,
                 x_glob = nof_inference(x2, img_ind, nof_embeddings, fw)
         return x_can, x_loc, x_glob
 
+    # fused form: statistics now, ONE all-reduce over the data-parallel ranks and the means at the end of the call
+    fused = ops.ResidualMeans(dev) if fused_residual_mean else None
+
     def residuals(result, tag, x_obs, x_loc, x_glob, alphas):
-        if chain_local:
-            result['nof_local_disp_' + tag] = ops.flow_residual(x_obs, x_loc, alphas, fused_residual_mean)
-        if chain_global:
-            result['nof_global_disp_' + tag] = ops.flow_residual(x_obs, x_glob, alphas, fused_residual_mean)
+        for on, name, x_rec in ((chain_local, 'nof_local_disp_', x_loc), (chain_global, 'nof_global_disp_', x_glob)):
+            if not on:
+                continue
+            if fused is not None:
+                result[name + tag] = None       # keeps the reference's key order; filled by fused.finish
+                fused.add(name + tag, x_obs, x_rec, alphas)
+            else:
+                result[name + tag] = ops.flow_residual(x_obs, x_rec, alphas, False)
 
     if use_nof:
         nerf_in, x_loc, x_glob = flow_chain(xyz_coarse)
@@ -172,4 +182,6 @@ def _render_rays(rays, background, nerf_embeddings, nerf_models, nof_embeddings,
         result['opacity_fine'] = opacity_fine
         if use_nof and not test_time:
             residuals(result, 'fine', xyz_fine, x_loc_f, x_glob_f, alphas_fine)
+    if fused is not None:
+        fused.finish(result)
     return result

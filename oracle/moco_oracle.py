@@ -234,9 +234,9 @@ def sample_pdf(bins: Tensor, weights: Tensor, n_importance: int, det: bool = Fal
     cdf = torch.cumsum(pdf, dim=-1)  # :22
     cdf = torch.cat([torch.zeros_like(cdf[:, :1]), cdf], dim=-1)  # :23
     if det:
-        u = torch.linspace(0, 1, n_importance).expand(n_rays, n_importance)  # :27-28
+        u = torch.linspace(0, 1, n_importance, device=bins.device).expand(n_rays, n_importance)  # :27-28
     elif u is None:
-        u = torch.rand(n_rays, n_importance)  # :30
+        u = torch.rand(n_rays, n_importance, device=bins.device)  # :30
     u = u.contiguous()
     inds = torch.searchsorted(cdf, u, right=True)  # :33
     below = (inds - 1).clamp(min=0)  # :34

@@ -69,7 +69,12 @@ def _worker_flat(rank, world, port, out):
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
     # flattened parameters: one broadcast of the flat buffer makes every rank identical
     flat = dp.FlatGradients([net], flatten_params=True)
+    from moco_flow_b200 import ops
+    epoch0 = ops.PARAM_EPOCH
     flat.broadcast_parameters(src=0)
+    assert ops.PARAM_EPOCH > epoch0          # packed bf16 weight images must be rebuilt after a p.data write
+    dp.enable_global_residual_means()
+    assert ops.RESIDUAL_DP is not None and ops.RESIDUAL_DP[1] == world
     gen = torch.Generator().manual_seed(123)
     rays = torch.randn(10, 6, generator=gen)
     target = torch.randn(10, 3, generator=gen)
@@ -94,3 +99,37 @@ def test_two_rank_flat_parameters_and_sum_allreduce(tmp_path):
     torch.nn.functional.mse_loss(net(blob["rays"]), blob["target"]).backward()
     ref = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
     assert torch.allclose(blob["grad"], ref, atol=1e-6)
+
+
+def test_zero_grad_keeps_flat_views():
+    """FusedAdam.zero_grad() must zero in place (torch's default drops .grad, after which the backward
+    would write gradients the flat all-reduce buffer never sees); a dropped view is reported, not ignored."""
+    from moco_flow_b200.optim import FusedAdam
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    flat = dp.FlatGradients([net])
+    opt = FusedAdam(flat.params, lr=1e-3)
+    torch.nn.functional.mse_loss(net(torch.randn(4, 6)), torch.randn(4, 3)).backward()
+    assert float(flat.buffer.abs().sum()) > 0
+    opt.zero_grad()
+    assert float(flat.buffer.abs().sum()) == 0
+    flat.check_views()
+    with pytest.raises(RuntimeError):
+        opt.zero_grad(set_to_none=True)
+    net[0].weight.grad = None
+    with pytest.raises(RuntimeError):
+        flat.allreduce_sum()
+
+
+def test_embedding_device_table_tracks_weights():
+    """the encoder weights the kernels read live in a device table that follows ``Embedding.weights``
+    (CPU check of the host logic with a CPU 'device')."""
+    import moco_flow_b200 as mf
+    from moco_flow_b200 import _lib as L
+    e = mf.Embedding(3, 4)
+    t = e.device_table("cpu")
+    assert t.shape == (2 * L.MAX_FREQS,) and t[:4].tolist() == [1, 2, 4, 8] and t[L.MAX_FREQS:L.MAX_FREQS + 4].tolist() == [1] * 4
+    ptr = t.data_ptr()
+    e.weights = [1.0, 0.5, 0.0, 0.0]         # what the coarse-to-fine schedule does every step
+    e.sync_device()
+    t2 = e.device_table("cpu")
+    assert t2.data_ptr() == ptr and t2[L.MAX_FREQS:L.MAX_FREQS + 4].tolist() == [1.0, 0.5, 0.0, 0.0]

@@ -302,3 +302,39 @@ def test_fine_pass_at_reference_samples(dev, golden_dir):
     assert rel.median().item() <= 2e-3 and rel.max().item() <= 5e-3
     e, _ = stats("fine pass @ reference samples: weights", w, w_o)
     assert e <= 2e-2  # per-sample weights are the most sensitive quantity (a 0.5% density error on one dense sample)
+
+
+def test_graph_replay_follows_embedding_weights(dev):
+    """the coarse-to-fine schedule re-assigns Embedding.weights every step
+    (trainer/trainer_moco_flow.py:280-305).  The kernels read the per-frequency weights from a device table, so a
+    captured graph replays with the CURRENT weights once the table is refreshed (CudaGraphStep(refresh=...))."""
+    import moco_flow_b200 as mf
+    from moco_flow_b200.graph import CudaGraphStep
+    gen = torch.Generator().manual_seed(9)
+    R, S = 16, 32
+    xyz = ((torch.rand(R * S, 3, generator=gen) - 0.5) * 2.0).to(dev)
+    ind = (torch.rand(R, 1, generator=gen) * 2 - 1).to(dev)
+    m = mf.NeRF(8, 256, 63, [4], "ind", 5)
+    m.load_state_dict(orc.make_nerf_params(orc.C2F_NERF, 5, dense=True))
+    m = m.to(dev)
+    pe, pe_i = mf.Embedding(3, 10), mf.Embedding(1, 2)
+
+    def fn(x):
+        with torch.no_grad():
+            return m.evaluate(xyz=x, pe=pe, ray_feat=pe_i(ind), rows_per_ray=S)
+
+    step = CudaGraphStep(fn, [xyz], warmup=1, refresh=[pe, pe_i])
+    full = step(xyz).clone()
+    assert torch.equal(full, fn(xyz))
+    pe.weights = [1.0, 1.0, 1.0, 0.5] + [0.0] * 6      # c2f: high frequencies faded out
+    replay = step(xyz).clone()
+    eager = fn(xyz)
+    torch.cuda.synchronize()
+    _no_device_error()
+    assert torch.equal(replay, eager)
+    assert not torch.equal(replay, full)
+    feats = torch.cat([orc.positional_encoding(xyz.cpu(), orc.PESpec(3, 10, weights=tuple(pe.weights))),
+                       orc.positional_encoding(ind.cpu(), orc.PESpec(1, 2)).repeat_interleave(S, 0)], 1)
+    ref = orc.nerf_mlp(orc.make_nerf_params(orc.C2F_NERF, 5, dense=True), orc.C2F_NERF, feats)
+    e, _ = stats("graph replay with faded PE weights: rgb", replay[:, :3], ref[:, :3])
+    assert e <= 2e-3

@@ -142,7 +142,7 @@ def test_plans_carry_their_program_family():
     assert all(int(e) < 16 for e in nf.rounds["epi"]) and all(int(e) >= 16 for e in nb.rounds["epi"])
     assert int(of.rounds["epi"][-1]) == L.EPI_NOF_HEAD
     names = [f[0] for f in L.ChainParams._fields_]
-    assert names[-2:] == ["cta_pair", "program_kind"]
+    assert names[-3:] == ["cta_pair", "program_kind", "pe_table"]
 
 
 def test_bench_reference_arm_contract():
