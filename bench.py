@@ -1,15 +1,19 @@
 #!/usr/bin/env python
 """Benchmark of the MoCo-Flow ray-rendering hot path (contract: see the task statement / DESIGN.md).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|render]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
 
 A step of the default workload (BASELINE.json configs[2], the one the headline metric "train rays/s
 (fwd+bwd, 64+64 spp)" is quoted on) is one MoCo-Flow training step on 4096 synthetic rays per GPU:
 render_rays with both flow chains (5 NoF + 1 NeRF evaluations per sample, coarse 64 + fine 64 samples),
 image MSE + 0.2 local + 0.2 global chain losses, backward, NCCL all-reduce of the flat gradient buffer
-(N > 1) and one Adam step.  ``--workload render`` times configs[1] (4096-ray inference render).
+(N > 1) and one Adam step.  Other workloads (the remaining BASELINE.json configs, not the driver's bench line):
+``cfg1`` configs[0] (canonical NeRF only, 1024 rays), ``render`` configs[1] (4096-ray MoCo-Flow render),
+``frame`` configs[3] (one 540x540 frame per step, rays sharded over the GPUs, result gathered; 16 steps = the
+16-frame job), ``stress`` configs[4] (1080x1080, 128+128, forward-o-backward flow consistency, sharded + gathered).
 
-Prints ONE JSON line.  ``--impl reference`` times the CPU oracle port of the reference on the host cores.
+Prints ONE JSON line.  ``--impl reference`` times the CPU oracle port of the reference on the host cores
+(``--device cuda [--tf32]`` runs the same eager-PyTorch port on one B200: "the reference on the same silicon").
 """
 from __future__ import annotations
 
@@ -31,8 +35,16 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 RAYS_PER_GPU = 4096
-N_COARSE, N_FINE = 64, 64
+N_COARSE, N_FINE = 64, 64     # rebound by set_workload() for the stress workload
 N_FRAMES = 160
+FRAME_HW = {"frame": (540, 540), "stress": (1080, 1080)}
+CHUNK_RAYS = 1 << 17          # rays per render_rays call inside a full-frame step (the reference's inference loop
+                              # chunks the same way, trainer/trainer_moco_flow.py:590-626)
+
+
+def set_workload(workload: str) -> None:
+    global N_COARSE, N_FINE
+    N_COARSE, N_FINE = (128, 128) if workload == "stress" else (64, 64)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -48,12 +60,37 @@ def synth_batch(n_rays: int, seed: int):
     return rays, bg, target
 
 
+def render_kwargs(workload: str) -> dict:
+    """render_rays keyword arguments of a workload (both arms)."""
+    kw = dict(N_samples=N_COARSE, N_importance=N_FINE, perturb=1.0, noise_std=0.0)
+    if workload == "train":
+        kw.update(chain_local=True, chain_global=True)
+    elif workload == "stress":
+        kw.update(chain_local=True)        # forward-o-backward flow consistency pass, no grad
+    elif workload != "cfg1":
+        kw.update(test_time=True)
+    return kw
+
+
+def rays_per_rank(workload: str, rank: int, world: int) -> int:
+    if workload in FRAME_HW:               # one frame per step, contiguous ray ranges per GPU (strong scaling)
+        from moco_flow_b200 import dp
+        h, w = FRAME_HW[workload]
+        b, e = dp.shard_bounds(h * w, rank, world)
+        return e - b
+    return 1024 if workload == "cfg1" else RAYS_PER_GPU
+
+
 def algorithmic_flops_per_ray(workload: str) -> float:
     """un-padded reference shapes, 2*MAC; backward counted as 2x forward."""
     nerf, nerf_sigma, nof = 1181184.0, 982528.0, 134400.0
-    if workload == "render":  # test_time: sigma-only coarse + full fine, bw-NoF on every sample
-        return nof * (N_COARSE + N_COARSE + N_FINE) + nerf_sigma * N_COARSE + nerf * (N_COARSE + N_FINE)
     s_tot = N_COARSE + (N_COARSE + N_FINE)
+    if workload in ("render", "frame"):  # test_time: sigma-only coarse + full fine, bw-NoF on every sample
+        return nof * s_tot + nerf_sigma * N_COARSE + nerf * (N_COARSE + N_FINE)
+    if workload == "cfg1":               # canonical NeRF only, full coarse + full fine
+        return nerf * s_tot
+    if workload == "stress":             # bw then fw flow on every sample (chain_local), full coarse + fine NeRF
+        return 2 * nof * s_tot + nerf * s_tot
     return 3.0 * (5 * nof * s_tot + nerf * s_tot)
 
 
@@ -137,11 +174,9 @@ def self_check(workload, dev, nerfs, nofs, nerf_embs, nof_embs, n_rays: int = 25
     o_nerfs = [orc.NeRFBundle(orc.C2F_NERF, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}) for m in nerfs]
     o_nofs = [orc.NoFBundle(orc.C2F_NOF, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}) for m in nofs]
     train = workload == "train"
-    kw = dict(N_samples=N_COARSE, N_importance=N_FINE, perturb=1.0, noise_std=0.0)
-    if train:
-        kw.update(chain_local=True, chain_global=True)
-    else:
-        kw.update(test_time=True)
+    kw = render_kwargs(workload)
+    if workload == "cfg1":
+        nofs = nof_embs = o_nofs = None
     with torch.no_grad():
         res = mf.render_rays(rays.to(dev), bg.to(dev), nerf_embs, nerfs, nof_embeddings=nof_embs, nof_models=nofs,
                              draws=draws, fused_residual_mean=True, **kw)
@@ -153,12 +188,15 @@ def self_check(workload, dev, nerfs, nofs, nerf_embs, nof_embs, n_rays: int = 25
             orc.EMULATE_BF16 = mode != "fp32"
             try:
                 refs[mode] = orc.render_rays(rays, bg, [pes["nerf_xyz"], pes["nerf_ind"], None], o_nerfs,
-                                             [pes["nof_xyz"], pes["nof_ind"]], o_nofs, draws=dr, **kw)
+                                             [pes["nof_xyz"], pes["nof_ind"]] if o_nofs else None, o_nofs, draws=dr, **kw)
             finally:
                 orc.EMULATE_BF16 = False
-    for key in ("rgb_fine", "depth_fine", "opacity_fine"):
+    for key in sorted(res):
         for mode, ref in refs.items():
-            out[f"{key}_max_abs_vs_{mode}"] = float((res[key] - ref[key]).abs().max())
+            if "disp" in key:   # masked residual means: the oracle returns the dynamic-length vector
+                out[f"{key}_abs_vs_{mode}"] = abs(float(res[key].mean()) - float(ref[key].mean()))
+            else:
+                out[f"{key}_max_abs_vs_{mode}"] = float((res[key] - ref[key]).abs().max())
     if train:
         def objective(r, means):
             loss = ((r["rgb_coarse"] - tgt) ** 2).mean() + ((r["rgb_fine"] - tgt) ** 2).mean()
@@ -174,7 +212,9 @@ def self_check(workload, dev, nerfs, nofs, nerf_embs, nof_embs, n_rays: int = 25
     # turns alpha into the step function [sigma_last > 0]: a ray whose sigma_last is within bf16 rounding of zero may
     # legitimately flip, so the bound is on the fraction of rays, and the max is reported.
     bad = (res["rgb_fine"] - refs["bf16_emulated"]["rgb_fine"]).abs().amax(dim=1) > 1e-3
-    out["rgb_fine_rays_over_1e-3_vs_bf16_emulated"] = int(bad.sum())
+    if "rgb_coarse" in res:
+        bad = bad | ((res["rgb_coarse"] - refs["bf16_emulated"]["rgb_coarse"]).abs().amax(dim=1) > 1e-3)
+    out["rgb_rays_over_1e-3_vs_bf16_emulated"] = int(bad.sum())
     if float(bad.float().mean()) > 0.01:
         raise SystemExit(f"bench self-check failed: {out}")
     from moco_flow_b200 import _lib as L
@@ -209,10 +249,13 @@ def run_ours(args):
     nerfs, nofs, nerf_embs, nof_embs = build_models(dev)
     dp.broadcast_parameters(nerfs + nofs)
     train = args.workload == "train"
-    R = RAYS_PER_GPU
-    if args.workload == "frame":  # 540 x 540 pixels, contiguous ray ranges per GPU (strong scaling)
-        b, e = dp.shard_bounds(540 * 540, rank, world)
-        R = e - b
+    framed = args.workload in FRAME_HW
+    R = rays_per_rank(args.workload, rank, world)
+    r_max = rays_per_rank(args.workload, 0, world)   # first ranks hold the remainder: the gather pads to this
+    kw = render_kwargs(args.workload)
+    use_nofs = None if args.workload == "cfg1" else nofs
+    use_nof_embs = None if args.workload == "cfg1" else nof_embs
+    gathered = torch.empty(world * r_max, 5, device=dev) if framed else None
     # this rank's shard of the step's global batch (N * 4096 rays): weak scaling
     rays_h, bg_h, tgt_h = synth_batch(R, seed=1 + rank)
     rays_h, bg_h, tgt_h = rays_h.pin_memory(), bg_h.pin_memory(), tgt_h.pin_memory()
@@ -235,9 +278,24 @@ def run_ours(args):
             opt.step(grad_scale=flat.allreduce_sum())   # the 1/world of the gradient mean is folded into the update
             return loss.detach()
         with torch.no_grad():
-            res = mf.render_rays(rays, bg, nerf_embs, nerfs, nof_embeddings=nof_embs, nof_models=nofs,
-                                 N_samples=N_COARSE, N_importance=N_FINE, perturb=1.0, noise_std=0.0, test_time=True)
-        return res["rgb_fine"].mean()
+            if not framed:
+                res = mf.render_rays(rays, bg, nerf_embs, nerfs, nof_embeddings=use_nof_embs, nof_models=use_nofs,
+                                     fused_residual_mean=True, **kw)
+                return res["rgb_fine"].mean()
+            # full-frame step: this rank's contiguous ray range in chunks, then the result ([rgb, depth, opacity] =
+            # 20 B/ray) gathered on every rank -- the only communication of the inference partition
+            mine = torch.zeros(r_max, 5, device=dev) if R < r_max else torch.empty(r_max, 5, device=dev)
+            for b0 in range(0, R, CHUNK_RAYS):
+                sl = slice(b0, min(b0 + CHUNK_RAYS, R))
+                res = mf.render_rays(rays[sl], bg[sl], nerf_embs, nerfs, nof_embeddings=use_nof_embs,
+                                     nof_models=use_nofs, fused_residual_mean=True, **kw)
+                mine[sl, 0:3] = res["rgb_fine"]
+                mine[sl, 3] = res["depth_fine"]
+                mine[sl, 4] = res["opacity_fine"]
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, mine)
+                return gathered
+            return mine
 
     def sync_all():
         if world > 1:
@@ -254,7 +312,7 @@ def run_ours(args):
 
     dbg("warm-up done")
     parity = None
-    if rank == 0 and not args.no_self_check and args.workload in ("train", "render"):
+    if rank == 0 and not args.no_self_check:
         parity = self_check(args.workload, dev, nerfs, nofs, nerf_embs, nof_embs)
         dbg(f"self-check: {parity}")
     eager_step = step
@@ -295,7 +353,7 @@ def run_ours(args):
     # The 4096-ray render's working set (~30 MB) would sit in the 126 MB L2 from one step to the next: write a
     # 256 MB buffer between its timed steps and bracket every step with its own pair of events.  The training step
     # and the full-frame render stream several GB per step, far more than L2, and are timed back to back.
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.workload == "render" else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.workload in ("render", "cfg1") else None
 
     def timed_steps(fn):
         if flush is None:
@@ -322,7 +380,7 @@ def run_ours(args):
 
     # ---- end-to-end timing through the public API with host buffers ----
     sync_all()
-    loss_host = torch.empty((), pin_memory=True)
+    loss_host = torch.empty(world * r_max, 5, pin_memory=True) if framed else torch.empty((), pin_memory=True)
 
     def e2e_step():
         r = rays_h.to(dev, non_blocking=True)
@@ -398,7 +456,7 @@ def run_ours(args):
     tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json: sustained bf16, copy HBM)" if peaks else "fallback (B200_PROFILING.md)"
-    total_rays = (540 * 540 if args.workload == "frame" else world * R) * args.steps
+    total_rays = (FRAME_HW[args.workload][0] * FRAME_HW[args.workload][1] if framed else world * R) * args.steps
     kernels = {}
     for tag, d in agg.items():
         rate = d["work"] / (d["ms"] * 1e-3) if d["ms"] > 0 else 0.0
@@ -442,24 +500,20 @@ def run_ours(args):
                "ms_per_step": round(tm / 2, 4)}
         best = max(chain_tags, key=lambda t: agg[t]["work"] / max(agg[t]["ms"], 1e-9))
         mlp["best_kernel"] = roof(best)
-    flops_ray = algorithmic_flops_per_ray("train" if train else "render")
+    flops_ray = algorithmic_flops_per_ray(args.workload)
     h2d = int(rays_h.numel() + bg_h.numel() + tgt_h.numel()) * 4
     line = {
-        "metric": "train rays/s (fwd+bwd, 64+64 spp)" if train else "render rays/s (64+64 spp, test_time)",
+        "metric": metric_text(args.workload),
         "value": round(total_rays / (ms * 1e-3), 1), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-        "scaling": "strong" if args.workload == "frame" else "weak", "vs_baseline": None, "dtype": "bf16",
+        "scaling": "strong" if framed else "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": workload_text(args.workload),
-                   "rays_per_gpu": R, "n_coarse": N_COARSE, "n_fine": N_FINE,
-                   "l2": ("flushed: a 256 MB buffer is written between timed steps (outside the per-step events)"
-                          if args.workload == "render" else
-                          "no flush: one step streams several GB per GPU (saved operand images / sample tensors), "
-                          "far above the 126 MB L2"),
-                   "parallelism": f"dp{world} (rays sharded, weights replicated)",
-                   "cuda_graph": graphed},
+        "config": config_dict(args.workload, world),
+        "arm": {"rays_this_rank": R, "cuda_graph": graphed,
+                "gather": (f"all_gather of [rgb, depth, opacity] = 20 B/ray inside every timed step"
+                           if framed and world > 1 else None)},
         "e2e": {"value": round(total_rays / (ms_e2e * 1e-3), 1), "unit": "rays/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
+                "d2h_bytes_per_step": int(loss_host.numel()) * 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": launches,
         "parity": parity,
         "clocks": clk,
@@ -476,7 +530,7 @@ def run_ours(args):
             "what": "camera pose (3x4, passed by value) -> mcf_make_rays -> render_rays(test_time) -> mcf_canvas_scatter "
                     "-> rgb image copied to pinned host memory; max over ranks"}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.workload, sample_rays=args.cpu_rays, steps=1, warmup=1)
+        line["cpu_baseline"] = cpu_baseline(args.workload, sample_rays=args.cpu_rays, steps=5, warmup=2)
     print(json.dumps(line))
     finish()
 
@@ -484,55 +538,71 @@ def run_ours(args):
 # --------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle port of the reference on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_step_fn(workload: str, n_rays: int):
+def cpu_step_fn(workload: str, n_rays: int, device: str = "cpu"):
+    """One step of the workload on ``n_rays`` rays through the oracle port (plain eager PyTorch fp32: the reference's
+    algorithm op for op).  ``device='cuda'`` runs the same port on the GPU -- eager PyTorch on the same silicon."""
     from oracle import moco_oracle as orc
     torch.manual_seed(0)
     pes = orc.C2F_PE
     nerf_p = [orc.make_nerf_params(orc.C2F_NERF, s) for s in (1, 2)]
     nof_p = [orc.make_nof_params(orc.C2F_NOF, s) for s in (3, 4)]
     train = workload == "train"
-    if train:
-        for p in nerf_p + nof_p:
-            for k in p:
-                p[k].requires_grad_(True)
+    for p in nerf_p + nof_p:
+        for k in p:
+            p[k] = p[k].to(device).requires_grad_(train)
     nerfs = [orc.NeRFBundle(orc.C2F_NERF, p) for p in nerf_p]
-    nofs = [orc.NoFBundle(orc.C2F_NOF, p) for p in nof_p]
-    rays, bg, tgt = synth_batch(n_rays, seed=1)
+    nofs = [orc.NoFBundle(orc.C2F_NOF, p) for p in nof_p] if workload != "cfg1" else None
+    nof_pes = [pes["nof_xyz"], pes["nof_ind"]] if nofs else None
+    rays, bg, tgt = (t.to(device) for t in synth_batch(n_rays, seed=1))
     params = [v for p in nerf_p + nof_p for v in p.values()]
     opt = torch.optim.Adam(params, lr=5e-4, eps=1e-8) if train else None
+    kw = render_kwargs(workload)
 
     def step():
-        if train:
-            opt.zero_grad(set_to_none=True)
-            res = orc.render_rays(rays, bg, [pes["nerf_xyz"], pes["nerf_ind"], None], nerfs,
-                                  [pes["nof_xyz"], pes["nof_ind"]], nofs, chain_local=True, chain_global=True,
-                                  N_samples=N_COARSE, N_importance=N_FINE, perturb=1.0, noise_std=0.0)
-            loss = orc.train_objective(res, tgt)
-            loss.backward()
-            opt.step()
-            return float(loss.detach())
-        with torch.no_grad():
-            res = orc.render_rays(rays, bg, [pes["nerf_xyz"], pes["nerf_ind"], None], nerfs,
-                                  [pes["nof_xyz"], pes["nof_ind"]], nofs, N_samples=N_COARSE, N_importance=N_FINE,
-                                  perturb=1.0, noise_std=0.0, test_time=True)
-        return float(res["rgb_fine"].mean())
+        with torch.device(device):     # the port creates its linspace / rand / zeros tensors on the default device
+            if train:
+                opt.zero_grad(set_to_none=True)
+                res = orc.render_rays(rays, bg, [pes["nerf_xyz"], pes["nerf_ind"], None], nerfs, nof_pes, nofs, **kw)
+                loss = orc.train_objective(res, tgt)
+                loss.backward()
+                opt.step()
+                return float(loss.detach())
+            with torch.no_grad():
+                res = orc.render_rays(rays, bg, [pes["nerf_xyz"], pes["nerf_ind"], None], nerfs, nof_pes, nofs, **kw)
+            return float(res["rgb_fine"].mean())     # float(): also the device synchronisation of the cuda variant
     return step
+
+
+def time_cpu_steps(step, steps: int, warmup: int):
+    """(median s/step, all step times): warm-up steps untimed, every timed step measured on its own."""
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return statistics.median(ts), ts
 
 
 def cpu_baseline(workload: str, sample_rays: int, steps: int, warmup: int):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = cpu_step_fn(workload, sample_rays)
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
-    return {"value": round(sample_rays / dt, 2), "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{sample_rays} rays of the same workload per step ({steps} timed step(s), {warmup} warm-up), "
-                      f"{dt:.2f} s/step; the reference is a Python/PyTorch code base, so the CPU arm is the oracle "
-                      f"port (oracle/moco_oracle.py, torch fp32 eager, all host threads)"}
+    med, ts = time_cpu_steps(cpu_step_fn(workload, sample_rays), steps, warmup)
+    return {"value": round(sample_rays / med, 2), "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_rays} rays of the same workload per step (cost is linear in rays), median of {steps} timed "
+                      f"steps after {warmup} warm-up, {med:.2f} s/step; the reference is a Python/PyTorch code base, so "
+                      f"the CPU arm is the oracle port (oracle/moco_oracle.py, torch fp32 eager, all host threads)"}
+
+
+def metric_text(workload: str) -> str:
+    if workload == "train":
+        return "train rays/s (fwd+bwd, 64+64 spp)"
+    if workload == "stress":
+        return "render rays/s (128+128 spp, fw-o-bw flow consistency pass)"
+    if workload == "cfg1":
+        return "render rays/s (canonical NeRF only, 64+64 spp)"
+    return "render rays/s (64+64 spp, test_time)"
 
 
 def workload_text(workload: str) -> str:
@@ -542,9 +612,30 @@ def workload_text(workload: str) -> str:
                 "bw/fw NoF chains (local+global), random-init c2f.yaml shapes, Adam step, "
                 "ray-sharded DP + flat-gradient NCCL all-reduce")
     if workload == "frame":
-        return ("full-frame inference render (BASELINE configs[3] shape): 540x540 rays per step "
-                "sharded over the GPUs, 64+64 samples, test_time; ms_per_step = ms/frame")
+        return ("full-frame inference render (BASELINE configs[3]): one 540x540 frame per step (16 steps = the 16-frame "
+                "job), rays sharded over the GPUs, result gathered, 64+64 samples, test_time; ms_per_step = ms/frame")
+    if workload == "stress":
+        return ("stress render (BASELINE configs[4]): one 1080x1080 frame per step, 128+128 samples, bw-NoF -> NeRF plus "
+                "the forward-o-backward flow consistency pass (chain_local), no grad, rays sharded over the GPUs, "
+                "result gathered")
+    if workload == "cfg1":
+        return ("canonical NeRF render_rays forward (BASELINE configs[0]): 1024 rays, 64 coarse + 64 fine samples, "
+                "random-init 8x256 MLP, no flow networks")
     return "full MoCo-Flow ray render (BASELINE configs[1]): 4096 rays, 64+64 samples, test_time"
+
+
+def config_dict(workload: str, world: int) -> dict:
+    """``config`` of the JSON line -- identical in both arms (what differs between them is under ``arm``)."""
+    if workload in FRAME_HW:
+        rays = f"{FRAME_HW[workload][0] * FRAME_HW[workload][1]} per step over all GPUs"
+    else:
+        rays = f"{1024 if workload == 'cfg1' else RAYS_PER_GPU} per GPU per step"
+    return {"workload": workload_text(workload), "rays": rays, "n_coarse": N_COARSE, "n_fine": N_FINE,
+            "parallelism": f"dp{world} (rays sharded, weights replicated)",
+            "l2": ("GPU arm: a 256 MB buffer is written between timed steps (outside the per-step events)"
+                   if workload in ("render", "cfg1") else
+                   "GPU arm: no flush -- one step streams several GB per GPU (saved operand images / sample tensors), "
+                   "far above the 126 MB L2")}
 
 
 def run_reference(args):
@@ -553,27 +644,33 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n = args.cpu_rays
-    step = cpu_step_fn(args.workload, n)
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    train = args.workload == "train"
+    on_gpu = args.device == "cuda"
+    if on_gpu:
+        torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+        torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+    full = 1024 if args.workload == "cfg1" else RAYS_PER_GPU
+    n = min(args.cpu_rays, full) if not on_gpu else (args.cpu_rays if args.cpu_rays_given else full)
+    if args.workload in FRAME_HW and not args.cpu_rays_given:
+        n = 1024
+    med, ts = time_cpu_steps(cpu_step_fn(args.workload, n, "cuda" if on_gpu else "cpu"), args.steps, args.warmup)
+    dt = sum(ts)
     val = round(n * args.steps / dt, 2)
-    sample = (f"each step = {n} rays of the workload (bounded sample of the 4096-ray step; cost is linear in rays), "
-              f"oracle port on {torch.get_num_threads()} host threads")
+    where = (f"eager PyTorch on cuda:0 (TF32 {'on' if args.tf32 else 'off'})" if on_gpu
+             else f"{torch.get_num_threads()} host threads")
+    sample = (f"each step = {n} rays of the workload"
+              + ("" if n == full else " (bounded sample; cost is linear in rays)")
+              + f", oracle port on {where}; median step {med:.3f} s")
     line = {
         "impl": "reference",
-        "metric": "train rays/s (fwd+bwd, 64+64 spp)" if train else "render rays/s (64+64 spp, test_time)",
+        "metric": metric_text(args.workload),
         "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True,
+        "scaling": "strong" if args.workload in FRAME_HW else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_text(args.workload), "n_coarse": N_COARSE, "n_fine": N_FINE,
-                   "implementation": "CPU oracle port of the reference (oracle/moco_oracle.py, torch fp32 eager)",
-                   "rays_per_step": n},
+        "config": config_dict(args.workload, args.gpus),
+        "arm": {"implementation": "oracle port of the reference (oracle/moco_oracle.py, torch fp32 eager)",
+                "device": "cuda" if on_gpu else "cpu", "tf32": bool(args.tf32) if on_gpu else None, "rays_per_step": n,
+                "median_rays_per_s": round(n / med, 2)},
         "cpu_baseline": {"value": val, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -588,14 +685,23 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "render", "frame"],
-                    help="train: configs[2] step; render: configs[1] 4096-ray render; frame: one 540x540 frame "
-                         "(configs[3] shape) per step, rays sharded over the GPUs")
-    ap.add_argument("--cpu-rays", type=int, default=256, help="rays per CPU-baseline step (bounded sample)")
+    ap.add_argument("--workload", default="train", choices=["train", "render", "frame", "stress", "cfg1"],
+                    help="train: configs[2] step; render: configs[1] 4096-ray render; frame: one 540x540 frame per step "
+                         "(configs[3]; 16 steps = the 16-frame job); stress: configs[4] 1080x1080 128+128 with the "
+                         "flow-consistency pass; cfg1: configs[0] canonical NeRF only, 1024 rays")
+    ap.add_argument("--cpu-rays", type=int, default=None,
+                    help="rays per CPU-arm step (bounded sample; default 1024 = SURVEY 8d's slice)")
+    ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: run the eager-PyTorch port on the host (default) or on cuda:0")
+    ap.add_argument("--tf32", type=int, default=0, help="--impl reference --device cuda: allow TF32 matmuls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-self-check", action="store_true", help="skip the oracle comparison of the timed computation")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
+    args.cpu_rays_given = args.cpu_rays is not None
+    if args.cpu_rays is None:
+        args.cpu_rays = 1024
+    set_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -108,12 +108,21 @@ def _padded(feat: Tensor, width: int) -> Tensor:
 # features, the sigma / rgb heads, biases) stay fp32.  With the flag off (default) the functions
 # below are the reference's fp32 algorithm.
 EMULATE_BF16 = False
+# Sensitivity probe: multiply every value by (1 + EMULATE_NOISE * N(0,1)) BEFORE it is rounded to bf16.  1e-6 is the
+# size of an fp32 accumulation-order difference; two evaluations that differ only by that (this oracle vs a tensor
+# core, or two tensor-core kernels with different K-splits) round a small fraction of activations to different bf16
+# neighbours.  The tests use it to calibrate how far two faithful bf16 evaluations may be apart.
+EMULATE_NOISE = 0.0
+_NOISE_GEN = torch.Generator().manual_seed(20240229)
 
 
 def _r16(t: Tensor) -> Tensor:
     if not EMULATE_BF16:
         return t
-    return t + (t.to(torch.bfloat16).to(torch.float32) - t).detach()  # rounded value, straight-through gradient
+    src = t
+    if EMULATE_NOISE:
+        src = t.detach() * (1 + EMULATE_NOISE * torch.randn(t.shape, generator=_NOISE_GEN))
+    return t + (src.to(torch.bfloat16).to(torch.float32) - t).detach()  # rounded value, straight-through gradient
 
 
 def _tc_linear(x: Tensor, w: Tensor, b: Optional[Tensor], fp32_cols: Optional[slice] = None) -> Tensor:

@@ -112,13 +112,30 @@ def oracle_render_chunked(rays, bg, o_nerfs, o_nofs, draws, kw, chunk=1024):
     return {k: torch.cat(v) for k, v in per_ray.items()}, sums
 
 
-def record_outputs(tag, got, emu, ref, rec):
+def emulated_pair(rays, bg, o_nerfs, o_nofs, dr, kw, chunk=1024):
+    """The bf16-emulating oracle, and the same with 1e-6 relative noise before every rounding (the yardstick for how
+    far two faithful bf16 evaluations may be apart, scripts/depth_sensitivity.py)."""
+    orc.EMULATE_BF16 = True
+    try:
+        emu, sums = oracle_render_chunked(rays, bg, o_nerfs, o_nofs, dr, kw, chunk)
+        orc.EMULATE_NOISE = 1e-6
+        noisy, _ = oracle_render_chunked(rays, bg, o_nerfs, o_nofs, dr, kw, chunk)
+    finally:
+        orc.EMULATE_BF16, orc.EMULATE_NOISE = False, 0.0
+    return emu, sums, noisy
+
+
+def record_outputs(tag, got, emu, ref, rec, noisy=None):
     """Error figures of one output dict against the bf16-emulating and the fp32 oracle."""
     for k in sorted(ref):
         g, e, r = got[k].detach().cpu().double(), emu[k].double(), ref[k].double()
         rel32 = (g - r).abs() / r.abs().clamp_min(1e-3)
+        d16 = (g - e).abs().reshape(-1)
         rec[k] = {
-            "max_abs_vs_bf16_emulated": float((g - e).abs().max()),
+            "max_abs_vs_bf16_emulated": float(d16.max()),
+            "p99_abs_vs_bf16_emulated": float(d16.quantile(0.99)),
+            "p999_abs_vs_bf16_emulated": float(d16.quantile(0.999)),
+            "emulated_oracle_max_abs_vs_fp32": float((e - r).abs().max()),
             "max_abs_vs_fp32": float((g - r).abs().max()),
             "rel_vs_fp32_median": float(rel32.median()), "rel_vs_fp32_p999": float(rel32.quantile(0.999)),
             "rel_vs_fp32_max": float(rel32.max()),
@@ -126,6 +143,9 @@ def record_outputs(tag, got, emu, ref, rec):
             "emulated_oracle_rel_vs_fp32_max": float(((e - r).abs() / r.abs().clamp_min(1e-3)).max()),
             "ref_scale": float(r.abs().max()),
         }
+        if noisy is not None:
+            dn = (noisy[k].double() - e).abs().reshape(-1)
+            rec[k].update(emulated_self_noise_p99=float(dn.quantile(0.99)), emulated_self_noise_max=float(dn.max()))
         print(f"[scale] {tag}.{k}: " + ", ".join(f"{a}={b:.3e}" for a, b in rec[k].items()))
 
 
@@ -137,9 +157,15 @@ def assert_outputs(rec):
             assert v["max_abs_vs_bf16_emulated"] <= 5e-4, (k, v)
             assert v["max_abs_vs_fp32"] <= 2e-3, (k, v)      # north star: <= 2e-3 on rgb for the bf16 MLP path
         elif k.startswith("depth"):
-            assert v["max_abs_vs_bf16_emulated"] <= 1e-3 * max(v["ref_scale"], 1.0), (k, v)
-            # north star: <= 2e-3 on depth -- held at the median and at the 99.9th percentile ray; the max over 4096
-            # rays is bounded by what the bf16-emulating oracle itself deviates from fp32
+            # Depth of a random-init volume is the ill-conditioned output: an fp32 accumulation-order difference
+            # (1e-6) flips a few bf16 roundings, the density field (10 octaves of encoding) turns that into ~5e-3
+            # changes of single coarse weights, the inverse-cdf step moves fine samples by up to ~0.1 and depth by
+            # ~1e-2 on the worst rays (profiles/r02_depth_sensitivity.json).  So the yardstick is the emulating oracle's
+            # distance from its own 1e-6 perturbation: the kernel must be no further from the emulating oracle than 2x
+            # that (99th percentile and max); against fp32 the north-star 2e-3 (relative) is held at the median ray and
+            # the worst ray is no further from fp32 than 1.5x what the emulating oracle is.
+            assert v["p99_abs_vs_bf16_emulated"] <= 2 * v["emulated_self_noise_p99"] + 1e-4, (k, v)
+            assert v["max_abs_vs_bf16_emulated"] <= 2 * v["emulated_self_noise_max"] + 1e-4, (k, v)
             assert v["rel_vs_fp32_median"] <= 2e-3, (k, v)
             assert v["rel_vs_fp32_max"] <= max(2e-3, 1.5 * v["emulated_oracle_rel_vs_fp32_max"]), (k, v)
 
@@ -164,14 +190,10 @@ def test_cfg2_render_4096(dev):
     for k in runs[0]:   # the forward path has no atomics: two launches are bit-identical
         assert torch.equal(runs[0][k], runs[1][k]), k
     ref, _ = oracle_render_chunked(rays, bg, o_nerfs, o_nofs, dr, kw)
-    orc.EMULATE_BF16 = True
-    try:
-        emu, _ = oracle_render_chunked(rays, bg, o_nerfs, o_nofs, dr, kw)
-    finally:
-        orc.EMULATE_BF16 = False
+    emu, _, noisy = emulated_pair(rays, bg, o_nerfs, o_nofs, dr, kw)
     assert sorted(runs[0]) == sorted(ref)
     rec = RECORD.setdefault("cfg2_render_4096x64+64_test_time", {"deterministic": True})
-    record_outputs("cfg2", runs[0], emu, ref, rec)
+    record_outputs("cfg2", runs[0], emu, ref, rec, noisy)
     assert_outputs(rec)
 
 
@@ -231,7 +253,8 @@ def test_cfg3_train_4096(dev):
     ref, rsums, rloss, g32 = results["fp32"]
     emu, esums, eloss, gem = results["bf16_emulated"]
     got = {k: v for k, v in res.items() if "disp" not in k}
-    record_outputs("cfg3", got, emu, ref, rec)
+    _, _, noisy = emulated_pair(rays, bg, o_nerfs, o_nofs, dr, kw)
+    record_outputs("cfg3", got, emu, ref, rec, noisy)
     assert_outputs(rec)
     for k, (s, n) in esums.items():
         g = float(res[k].item())
@@ -246,15 +269,18 @@ def test_cfg3_train_4096(dev):
     assert abs(loss.item() - rloss) <= 2e-3 * max(1.0, abs(rloss))
     grec = rec.setdefault("gradients", {})
     for tag, mod, _ in mods:
+        for n, q in mod.named_parameters():
+            r16, r32 = gem[tag][n], g32[tag][n]
+            if r16 is None or q.grad is None:
+                continue
+            grec[f"{tag}.{n}"] = {"rel_fro_vs_bf16_emulated": rel_fro(q.grad, r16), "rel_fro_vs_fp32": rel_fro(q.grad, r32),
+                                  "cos_vs_fp32": cosine(q.grad, r32),
+                                  "emulated_oracle_rel_fro_vs_fp32": rel_fro(r16, r32)}
+    worst = max(grec.items(), key=lambda kv: kv[1]["rel_fro_vs_bf16_emulated"])
+    print(f"[scale] cfg3 gradients: worst rel Frobenius vs bf16-emulated {worst[0]} {worst[1]}")
+    for tag, mod, _ in mods:
         names = [n for n, _ in mod.named_parameters()]
         named_got = [(n, q.grad) for n, q in mod.named_parameters()]
-        for n, q in named_got:
-            r16, r32 = gem[tag][n], g32[tag][n]
-            if r16 is None or q is None:
-                continue
-            grec[f"{tag}.{n}"] = {"rel_fro_vs_bf16_emulated": rel_fro(q, r16), "rel_fro_vs_fp32": rel_fro(q, r32),
-                                  "cos_vs_fp32": cosine(q, r32),
-                                  "emulated_oracle_rel_fro_vs_fp32": rel_fro(r16, r32)}
         compare_grads(f"cfg3.{tag}", named_got, [(n, gem[tag][n]) for n in names], 5e-2,
                       [(n, g32[tag][n]) for n in names], min_cos=0.95)
 
@@ -277,13 +303,9 @@ def test_cfg5_shape_128_128_chain_local(dev):
     torch.cuda.synchronize()
     _no_device_error()
     ref, rsums = oracle_render_chunked(rays, bg, o_nerfs, o_nofs, dr, kw, chunk=256)
-    orc.EMULATE_BF16 = True
-    try:
-        emu, esums = oracle_render_chunked(rays, bg, o_nerfs, o_nofs, dr, kw, chunk=256)
-    finally:
-        orc.EMULATE_BF16 = False
+    emu, esums, noisy = emulated_pair(rays, bg, o_nerfs, o_nofs, dr, kw, chunk=256)
     rec = RECORD.setdefault("cfg5shape_512x128+128_chain_local", {})
-    record_outputs("cfg5", {k: v for k, v in res.items() if "disp" not in k}, emu, ref, rec)
+    record_outputs("cfg5", {k: v for k, v in res.items() if "disp" not in k}, emu, ref, rec, noisy)
     assert_outputs(rec)
     for k, (s, n) in esums.items():
         vec = res[k]
