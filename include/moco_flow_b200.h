@@ -202,11 +202,11 @@ typedef struct {
   uint32_t fwd_x0_off, fwd_he_off;
   float* d_xyz;            /* [M][3] grad w.r.t. the input points, or NULL   */
   float* d_head;           /* fp32 head gradients: NeRF [M][4] {d_pre_rgb(3), d_sigma}; NoF [M][12] {d v,s,t} */
-  /* per-ray features stored as a bf16 image block next to the saved operands (training forward), so
-   * that the weight-gradient GEMM sees the folded input columns */
-  const float* rayfeat;    /* [n_rays][rayfeat_stride]                       */
+  /* unused since ABI rev of round 2 (the per-ray feature images are built once per ray layout by
+   * mcf_rayfeat_image and shared by every evaluation, instead of being written by each chain launch) */
+  const float* rayfeat;
   int32_t rayfeat_stride, rayfeat_dim;
-  uint32_t extra_save_off; /* 0xFFFFFFFF none                                */
+  uint32_t extra_save_off;
   uint32_t dhead_save_off; /* backward: image block of the head gradients    */
   int32_t max_ctas;        /* 0 = one CTA per SM                             */
   /* optional instrumentation: [n_ctas][16] cycle counters (NULL = off):
@@ -224,6 +224,12 @@ typedef struct {
    * schedule (trainer/trainer_moco_flow.py:280-305); values passed by pointer stay current when the launch is
    * replayed from a captured CUDA graph, values passed in this struct are frozen at capture. */
   const float* pe_table;
+  /* resident != 0 (width 128, NoF programs): the program was built for the resident-weight kernel -- the whole packed
+   * weight stream (wpack_bytes <= 144 KB) is copied into shared memory once per CTA instead of being streamed per
+   * tile, and the first-layer operand shares the activation buffer (the plan precomputes the skip layer's x0 part in
+   * round 0).  Plans of the two kinds are not interchangeable. */
+  uint32_t wpack_bytes;
+  int32_t resident;
 } mcf_chain_params_t;
 
 int mcf_chain_launch(const mcf_chain_params_t* params_host, cudaStream_t stream);
@@ -253,10 +259,20 @@ typedef struct {
   int32_t ld, n_i, n_j;
   int32_t colsum_off;          /* float offset of colsum_p inside staging, or -1              */
   int32_t enabled;             /* 0: skip (parameter does not require grad)                   */
+  int32_t q_split;             /* the first q_split 64-column blocks of Q come from q_src, the rest from the
+                                * per-ray feature images (aux + tile*aux_tile_bytes + q2_off); -1: all from q_src */
+  uint32_t q2_off;
 } mcf_dw_job_t;
 int mcf_dw_gemm_batch(const mcf_dw_job_t* jobs_dev, int n_jobs, const void* fwd_save, long long fwd_tile_bytes,
-                      const void* bwd_save, long long bwd_tile_bytes, float* staging, long long n_tiles,
-                      int ctas_per_job, cudaStream_t stream);
+                      const void* bwd_save, long long bwd_tile_bytes, const void* aux, long long aux_tile_bytes,
+                      float* staging, long long n_tiles, int ctas_per_job, cudaStream_t stream);
+
+/* Per-ray feature columns (index / direction embedding, constant along a ray: models/rendering.py:73-75,133-142) as
+ * bf16 tile images [n_tiles][128 rows][64 cols] -- the Q operand of the weight gradients of the folded input
+ * columns.  It depends only on (features, rows_per_ray, n_rows), so one render call builds it once per ray layout
+ * and every MLP evaluation of that layout shares it (instead of every chain launch writing its own copy). */
+int mcf_rayfeat_image(const float* rayfeat, int rayfeat_stride, int rayfeat_dim, long long n_rows, int rows_per_ray,
+                      void* out, cudaStream_t stream);
 
 /* Scatter the staging results of mcf_dw_gemm into the parameter-gradient buffer:
  * dst[dst_off + r*dst_ld + c] = transposed ? src[src_off + c*src_ld + r] : src[src_off + r*src_ld + c]. */

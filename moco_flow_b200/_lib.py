@@ -35,9 +35,9 @@ UNPACK_DT = np.dtype([("src_off", "<u4"), ("dst_off", "<u4"), ("src_ld", "<i4"),
                       ("ncols", "<i4"), ("transposed", "<i4"), ("reserved", "<i4")])
 DWJOB_DT = np.dtype([("p_off", "<u4"), ("q_off", "<u4"), ("p_src", "<i4"), ("q_src", "<i4"), ("p_cols", "<i4"),
                      ("q_cols", "<i4"), ("st_off", "<u4"), ("ld", "<i4"), ("n_i", "<i4"), ("n_j", "<i4"),
-                     ("colsum_off", "<i4"), ("enabled", "<i4")])
+                     ("colsum_off", "<i4"), ("enabled", "<i4"), ("q_split", "<i4"), ("q2_off", "<u4")])
 MAX_UNPACK_PTRS = 40
-assert DWJOB_DT.itemsize == 48
+assert DWJOB_DT.itemsize == 56
 assert CHUNK_DT.itemsize == 16 and ROUND_DT.itemsize == 32 and PACK_DT.itemsize == 40 and UNPACK_DT.itemsize == 32
 
 _vp, _i32, _i64, _u32, _f32 = C.c_void_p, C.c_int32, C.c_longlong, C.c_uint32, C.c_float
@@ -57,6 +57,7 @@ class ChainParams(C.Structure):
         ("d_xyz", _vp), ("d_head", _vp), ("rayfeat", _vp), ("rayfeat_stride", _i32), ("rayfeat_dim", _i32),
         ("extra_save_off", _u32), ("dhead_save_off", _u32), ("max_ctas", _i32),
         ("timing", _vp), ("cta_pair", _i32), ("program_kind", _i32), ("pe_table", _vp),
+        ("wpack_bytes", _u32), ("resident", _i32),
     ]
 
 
@@ -72,7 +73,7 @@ class DwParams(C.Structure):
 EXPORTS = [
     "mcf_abi_version", "mcf_device_error_flag", "mcf_coarse_samples", "mcf_ray_points", "mcf_pe_fwd", "mcf_pe_bwd",
     "mcf_ray_bias", "mcf_composite_fwd", "mcf_composite_bwd", "mcf_sample_pdf", "mcf_masked_l1_fwd",
-    "mcf_masked_l1_finalize", "mcf_masked_l1_bwd", "mcf_pack", "mcf_chain_launch", "mcf_dw_gemm", "mcf_dw_gemm_batch", "mcf_unpack",
+    "mcf_masked_l1_finalize", "mcf_masked_l1_bwd", "mcf_pack", "mcf_chain_launch", "mcf_dw_gemm", "mcf_dw_gemm_batch", "mcf_rayfeat_image", "mcf_unpack",
     "mcf_unpack_accumulate", "mcf_colsum", "mcf_adam_step", "mcf_make_rays", "mcf_canvas_scatter", "mcf_nearest_vertex",
 ]
 

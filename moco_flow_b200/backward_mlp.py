@@ -61,8 +61,22 @@ def dw_ctas_per_job(device) -> int:
     return max(2, torch.cuda.get_device_properties(device).multi_processor_count // 2)
 
 
+def rayfeat_images(rf: torch.Tensor, n_rows: int, rows_per_ray: int) -> torch.Tensor:
+    """bf16 tile images [n_tiles][128][64] of the per-ray feature columns: the Q operand of the weight gradients of the
+    folded input columns.  Depends only on (features, ray layout): built once per render call per layout and shared by
+    all evaluations (coarse/fine pass x 5 flow evaluations + NeRF used to write one copy each)."""
+    from .mlp import memoised, _tkey
+    def make():
+        out = torch.empty(_n_tiles(n_rows) * L.BLOCK_BYTES, dtype=torch.uint8, device=rf.device)
+        L.check(L.lib().mcf_rayfeat_image(L.ptr(rf), C.c_int(rf.stride(0)), C.c_int(rf.shape[1]), C.c_longlong(n_rows),
+                                          C.c_int(rows_per_ray), L.ptr(out), L.stream_ptr()), "mcf_rayfeat_image")
+        return out
+    return memoised(("rfimg", _tkey(rf), n_rows, rows_per_ray), (rf,), make)
+
+
 def _run_grad_plan(model, gp: P.GradPlan, st, need_dx: bool, fwd_save: torch.Tensor, fwd_tile_bytes: int,
-                   bwd_save: torch.Tensor, bwd_tile_bytes: int, n_tiles: int, d_head: torch.Tensor, wanted: set):
+                   bwd_save: torch.Tensor, bwd_tile_bytes: int, n_tiles: int, d_head: torch.Tensor, wanted: set,
+                   aux: Optional[torch.Tensor] = None):
     """Runs the weight-gradient GEMMs; returns the flat gradient buffer, or None when the gradients were
     accumulated in place."""
     dev = fwd_save.device
@@ -77,6 +91,7 @@ def _run_grad_plan(model, gp: P.GradPlan, st, need_dx: bool, fwd_save: torch.Ten
     with L.timed("dw_gemm", work, "byte"):
         L.check(L.lib().mcf_dw_gemm_batch(L.ptr(jobs_dev), C.c_int(len(gp.jobs)), L.ptr(fwd_save),
                                           C.c_longlong(fwd_tile_bytes), L.ptr(bwd_save), C.c_longlong(bwd_tile_bytes),
+                                          L.ptr(aux), C.c_longlong(L.BLOCK_BYTES),
                                           L.ptr(staging), C.c_longlong(n_tiles), C.c_int(dw_ctas_per_job(staging.device)), L.stream_ptr()),
                 "mcf_dw_gemm_batch")
     ncols, stride, hc = gp.head_colsum
@@ -141,8 +156,6 @@ class _NeRFFn(torch.autograd.Function):
                 rf = rf.contiguous()
             rb = fold_bias(lin.weight, model.W, lin.bias, rf)
             cp.raybias[0] = rb.data_ptr()
-            cp.rayfeat, cp.rayfeat_stride, cp.rayfeat_dim = rf.data_ptr(), rf.stride(0), rf.shape[1]
-            cp.extra_save_off = plan.offsets["save_extra"]
             keep += [rb, rf]
         nt = _n_tiles(M)
         save = torch.empty(nt * plan.save_tile_bytes, dtype=torch.uint8, device=dev)
@@ -156,6 +169,7 @@ class _NeRFFn(torch.autograd.Function):
         ctx.model, ctx.pe, ctx.names, ctx.M, ctx.S = model, pe, names, M, rows_per_ray
         ctx.dense_mode = dense is not None
         ctx.need_dx = xyz is not None and xyz.requires_grad
+        ctx.aux = rayfeat_images(rf, M, rows_per_ray) if rf is not None else None
         ctx.save_for_backward(save, masks, out)
         return out
 
@@ -205,7 +219,7 @@ class _NeRFFn(torch.autograd.Function):
         if wanted:
             gp = st.grad[need_dx]
             flat = _run_grad_plan(model, gp, st, need_dx, save, fwd_plan.save_tile_bytes, bsave,
-                                  bplan.save_tile_bytes, nt, d_head, wanted)
+                                  bplan.save_tile_bytes, nt, d_head, wanted, ctx.aux)
             if flat is not None:
                 pgrads = _param_grads(gp, flat, ctx.names, needs)
         return (None, None, None, d_xyz, None, None, None, *pgrads)
@@ -256,12 +270,11 @@ class _NoFFn(torch.autograd.Function):
                 rb = fold_bias(lin.weight, cx, lin.bias, rf)
                 cp.raybias[k] = rb.data_ptr()
                 keep.append(rb)
-            cp.rayfeat, cp.rayfeat_stride, cp.rayfeat_dim = rf.data_ptr(), rf.stride(0), rf.shape[1]
-            cp.extra_save_off = plan.offsets["save_extra"]
             keep.append(rf)
+        else:   # the layer-1 weight GEMM still reads a (zero) feature block
+            rf = torch.zeros(R, 1, device=dev)
         nt = _n_tiles(M)
-        # the per-ray feature block must exist (zeros) even when E == 0, because the layer-1 weight GEMM reads it
-        save = (torch.empty if E > 0 else torch.zeros)(nt * plan.save_tile_bytes, dtype=torch.uint8, device=dev)
+        save = torch.empty(nt * plan.save_tile_bytes, dtype=torch.uint8, device=dev)
         masks = torch.empty(nt * plan.mask_tile_words, dtype=torch.int32, device=dev)
         out = torch.empty(M, 3, device=dev)
         head_save = torch.empty(M, 12, device=dev)
@@ -272,6 +285,7 @@ class _NoFFn(torch.autograd.Function):
         cp.x0_save_off = plan.offsets["save_x0"]
         ops.launch_chain(cp, "nof_fwd", ops.linear_flops(model))
         ctx.model, ctx.pe, ctx.names, ctx.M, ctx.S = model, pe, names, M, rows_per_ray
+        ctx.aux = rayfeat_images(rf, M, rows_per_ray)
         ctx.need_dx = xyz.requires_grad
         ctx.save_for_backward(save, masks, head_save)
         return out
@@ -322,7 +336,7 @@ class _NoFFn(torch.autograd.Function):
         if wanted:
             gp = st.grad[need_dx]
             flat = _run_grad_plan(model, gp, st, need_dx, save, fwd_plan.save_tile_bytes, bsave,
-                                  bplan.save_tile_bytes, nt, d_head, wanted)
+                                  bplan.save_tile_bytes, nt, d_head, wanted, ctx.aux)
             if flat is not None:
                 pgrads = _param_grads(gp, flat, ctx.names, needs)
         return (None, None, None, d_xyz, None, None, None, *pgrads)

@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/moco_flow_b200.h"
 #include "ptx.cuh"
 
@@ -45,8 +47,9 @@ struct Tables {
   uint64_t w_peer[kMaxStages];  // CTA pairs: the peer's half of a ring stage has landed (leader CTA only)
   uint64_t act_ready[2];
   uint64_t acc_full[2];
+  uint64_t w_res;               // resident variant: the weight stream has landed
   uint32_t tmem_base;
-  uint32_t pad[3];
+  uint32_t pad[1];
   float pe_freq[12];    // encoder tables: from the launch parameters, or from p.pe_table (device) when given
   float pe_weight[12];
 };
@@ -63,6 +66,24 @@ struct Smem {
   static constexpr uint32_t total = off_tab + sizeof(Tables);
 };
 static_assert(Smem<256>::total <= 232448 && Smem<128>::total <= 232448, "shared memory budget exceeded");
+
+// Resident-weight variant (NoF, W = 128): the whole packed weight stream of the program (<= 144 KB) is copied into
+// shared memory once per CTA; there is no ring, no producer and no per-tile weight traffic.  The first-layer operand
+// (x0) lives in block 0 of the slot's activation buffer (the round-0 epilogue overwrites it once the tensor core has
+// consumed it), which is what makes two slots + the weights fit.
+constexpr uint32_t kResBytes = 147456;
+template <int W>
+struct SmemRes {
+  static constexpr int kStages = 1;
+  static constexpr uint32_t kHBlocks = W / 64;
+  static constexpr uint32_t kHBytes = kHBlocks * kBlk;
+  static constexpr uint32_t off_h = 0;
+  static constexpr uint32_t off_x0 = 0;                       // aliased: slot s -> off_h + s * kHBytes
+  static constexpr uint32_t off_ring = off_h + 2 * kHBytes;   // the resident weights
+  static constexpr uint32_t off_tab = off_ring + kResBytes;
+  static constexpr uint32_t total = off_tab + sizeof(Tables);
+};
+static_assert(SmemRes<128>::total <= 232448, "shared memory budget exceeded");
 
 // ---------------------------------------------------------------------------------------------
 // epilogue helpers (thread == row)
@@ -238,8 +259,10 @@ __device__ __forceinline__ void nof_quat_backward(const float* h9, const float* 
 // kSave: the launch writes training saves (operand images, ReLU masks, head values); inference instantiations carry
 // none of that code.  The in-kernel cycle counters exist only in builds with -DMCF_TIMING (scripts/chain_timing.py).
 // kNoF: NoF program (flow head, quaternion transform) vs NeRF program (sigma / rgb heads).
-template <int W, int C, bool kBwd, bool kSave, bool kNoF>
+// kRes: resident-weight variant (SmemRes): W = 128, C = 1 only.
+template <int W, int C, bool kBwd, bool kSave, bool kNoF, bool kRes = false>
 __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ mcf_chain_params_t p) {
+  static_assert(!kRes || (W == 128 && C == 1), "resident weights: W = 128, single CTA");
   extern __shared__ __align__(1024) uint8_t smem[];
 #ifdef MCF_TIMING
   const bool timing = p.timing != nullptr;
@@ -248,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
 #endif
   unsigned long long tacc[4] = {0ull, 0ull, 0ull, 0ull};
   const long long t_kernel0 = timing ? clock64() : 0;
-  using L = Smem<W>;
+  using L = typename std::conditional<kRes, SmemRes<W>, Smem<W>>::type;
   constexpr int kStages = L::kStages;
   Tables& tab = *reinterpret_cast<Tables*>(smem + L::off_tab);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -272,8 +295,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       tab.pe_freq[k] = p.pe_table ? p.pe_table[k] : p.pe_freq[k];
       tab.pe_weight[k] = p.pe_table ? p.pe_table[MCF_MAX_FREQS + k] : p.pe_weight[k];
     }
-    uint4* x0z = reinterpret_cast<uint4*>(smem + L::off_x0);
-    for (int i = threadIdx.x; i < (int)(2 * kBlk / 16); i += kThreads) x0z[i] = make_uint4(0, 0, 0, 0);
+    if (!kRes) {
+      uint4* x0z = reinterpret_cast<uint4*>(smem + L::off_x0);
+      for (int i = threadIdx.x; i < (int)(2 * kBlk / 16); i += kThreads) x0z[i] = make_uint4(0, 0, 0, 0);
+    }
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -285,7 +310,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       mbar_init(&tab.act_ready[s], C == 2 ? 8 : 128);  // pairs: one arrival per epilogue warp of both CTAs, on the leader's barrier
       mbar_init(&tab.acc_full[s], 1);
     }
+    mbar_init(&tab.w_res, 1);
     fence_mbar_init();
+    if (kRes) {   // the whole weight stream, once (32 KB pieces; the mbarrier counts the bytes)
+      const uint32_t total = p.wpack_bytes;
+      mbar_arrive_expect_tx(&tab.w_res, total);
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack);
+      for (uint32_t off = 0; off < total; off += 32768u) {
+        const uint32_t n = total - off < 32768u ? total - off : 32768u;
+        bulk_g2s(smem + L::off_ring + off, wsrc + off, n, &tab.w_res);
+      }
+    }
   }
   if (warp == 2) {
     if (C == 2) {
@@ -324,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     // =========================== weight producers (warps 0, 2, 3) ===========================
     // Every producer walks the whole copy sequence (to track stage / phase) and issues every kProducers-th copy.
     const int me = (warp == 0) ? 0 : warp - 1;
-    if (lane == 0 && me < kProducers) {
+    if (!kRes && lane == 0 && me < kProducers) {
       int turn = 0;
       uint32_t stage = 0, phase = 0;
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack);
@@ -385,6 +420,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       uint32_t ar_phase[2] = {0u, 0u};
       const uint32_t h_addr = smem_u32(smem + L::off_h), x0_addr = smem_u32(smem + L::off_x0);
       const uint32_t ring_addr = smem_u32(smem + L::off_ring);
+      if (kRes) {
+        mbar_wait(&tab.w_res, 0u, 0x700u);
+        tc_fence_after();
+      }
       for (long long pair = unit0; pair < n_pairs; pair += unit_step) {
         for (int r = 0; r < p.n_rounds; ++r) {
           const int cb = tab.rounds[r].chunk_begin, ce = tab.rounds[r].chunk_end;
@@ -396,17 +435,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             tc_fence_after();
             MCF_TACC(0, tm);
             for (int c = cb; c < ce; ++c) {
-              mbar_wait(&tab.w_full[stage], phase, 0x300u | stage);
+              if (!kRes) mbar_wait(&tab.w_full[stage], phase, 0x300u | stage);
               const mcf_chunk_t ch = tab.chunks[c];
               // flag bit1: this chunk and the next one are the two 128-row halves of one [256 x 64] weight tile
               // sitting in consecutive (even, odd) ring stages -> one N=256 instruction per K step
-              const bool fuse = (ch.flags & 2u) != 0u;
+              const bool fuse = (ch.flags & 2u) != 0u;   // resident variant: the two images are adjacent in the stream
               if (C == 2) mbar_wait(&tab.w_peer[stage], phase, 0x600u | stage);
-              else if (fuse) mbar_wait(&tab.w_full[stage + 1], phase, 0x300u | (stage + 1));
-              tc_fence_after();
+              else if (fuse && !kRes) mbar_wait(&tab.w_full[stage + 1], phase, 0x300u | (stage + 1));
+              if (!kRes) tc_fence_after();
               MCF_TACC(1, tm);
-              const uint32_t a_base = (ch.a_buf ? (h_addr + s * L::kHBytes) : (x0_addr + s * kBlk)) + ch.a_kblock * kBlk;
-              const uint32_t b_base = ring_addr + stage * kBlk;
+              // resident variant: x0 is block 0 of the slot's activation buffer, weights sit at their stream offset
+              const uint32_t a_base = ((ch.a_buf || kRes) ? (h_addr + s * L::kHBytes) : (x0_addr + s * kBlk)) + ch.a_kblock * kBlk;
+              const uint32_t b_base = kRes ? ring_addr + ch.src_off : ring_addr + stage * kBlk;
               const uint32_t idesc = make_idesc(fuse ? 2u * ch.n : (uint32_t)ch.n, false, false, 128u * C);
               const uint32_t d_tmem = tmem_base + s * kSlotCols + ch.acc_col;
               // one thread feeds the tensor core: keep the per-instruction work to two 64-bit adds (a K step of 16
@@ -426,7 +466,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
                   ad += 2u; bd += 2u; acc = 1u;
                 }
               }
-              if (C == 2) {
+              if (kRes) {
+                if (fuse) ++c;   // nothing to release
+              } else if (C == 2) {
                 umma_commit_pair(&tab.w_empty[stage], 3);   // frees the stage in both CTAs
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 if (fuse) ++c;
@@ -461,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     const uint32_t row = qtr * 32 + lane;   // tile row owned by this thread
     const int gtid = threadIdx.x - 128 - s * 128;
     uint8_t* hbuf = smem + L::off_h + s * L::kHBytes;
-    uint8_t* x0buf = smem + L::off_x0 + s * kBlk;
+    uint8_t* x0buf = kRes ? hbuf : smem + L::off_x0 + s * kBlk;
     const uint32_t t_row = tmem_base + ((uint32_t)(qtr * 32) << 16) + s * kSlotCols;
     const uint32_t act_ready_leader = (C == 2) ? map_to_cta(smem_u32(&tab.act_ready[s]), 0u) : 0u;
     auto arrive_act_ready = [&]() {
@@ -623,23 +665,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         for (int c8 = 2; c8 < 8; ++c8) store_h8(hbuf, row, c8 * 8, make_uint4(0, 0, 0, 0));
       } else {
         if (gtid == 0) atomicExch(&g_mcf_device_error, 0xBADF0000u | (uint32_t)p.prologue);
-      }
-      if (saving && p.extra_save_off != kNone && p.rayfeat != nullptr) {
-        // per-ray feature columns as an image block, written straight to the save record
-        const float* rf = p.rayfeat + ray * p.rayfeat_stride;
-        uint8_t* blk = save_tile + p.extra_save_off;
-        for (int c8 = 0; c8 < 8; ++c8) {
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = c8 * 8 + j;
-            f[j] = (valid && c < p.rayfeat_dim) ? __ldg(rf + c) : 0.f;
-          }
-          uint4 v;
-          v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
-          v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
-          *reinterpret_cast<uint4*>(blk + sw128_off(row, c8)) = v;
-        }
       }
       fence_proxy_async_smem();
       if (saving && p.x0_save_off != kNone) {
@@ -1062,6 +1087,10 @@ int mcf_chain_launch(const mcf_chain_params_t* pp, cudaStream_t stream) {
 #define MCF_PICK2(W_, C_, N_)                                                                             \
   (bwd ? (const void*)mcf::k_chain<W_, C_, true, true, N_>                                                \
        : (save ? (const void*)mcf::k_chain<W_, C_, false, true, N_> : (const void*)mcf::k_chain<W_, C_, false, false, N_>))
+#define MCF_PICK_RES()                                                                                    \
+  (bwd ? (const void*)mcf::k_chain<128, 1, true, true, true, true>                                        \
+       : (save ? (const void*)mcf::k_chain<128, 1, false, true, true, true>                               \
+               : (const void*)mcf::k_chain<128, 1, false, false, true, true>))
 #define MCF_PICK(W_, C_) (nof ? MCF_PICK2(W_, C_, true) : MCF_PICK2(W_, C_, false))
   const bool nof = p.program_kind == 1;
   if (p.program_kind != 0 && p.program_kind != 1) return MCF_ERR_BAD_ARG;
@@ -1072,6 +1101,11 @@ int mcf_chain_launch(const mcf_chain_params_t* pp, cudaStream_t stream) {
   } else if (p.width == 256) {
     fn = MCF_PICK(256, 1);
     smem = (int)mcf::Smem<256>::total;
+  } else if (p.width == 128 && p.resident) {
+    // the program was built for the resident-weight kernel (x0 aliased into the activation buffer): NoF only
+    if (!nof || p.wpack_bytes == 0 || p.wpack_bytes > mcf::kResBytes || (p.wpack_bytes & 15u)) return MCF_ERR_BAD_ARG;
+    fn = MCF_PICK_RES();
+    smem = (int)mcf::SmemRes<128>::total;
   } else if (p.width == 128) {
     fn = MCF_PICK(128, 1);
     smem = (int)mcf::Smem<128>::total;
@@ -1080,6 +1114,7 @@ int mcf_chain_launch(const mcf_chain_params_t* pp, cudaStream_t stream) {
   }
 #undef MCF_PICK2
 #undef MCF_PICK
+#undef MCF_PICK_RES
 #ifndef MCF_TIMING
   if (p.timing != nullptr) return MCF_ERR_UNSUPPORTED;   // cycle counters need a -DMCF_TIMING build
 #endif

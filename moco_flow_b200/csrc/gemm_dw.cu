@@ -39,16 +39,25 @@ constexpr uint32_t kDwSmem = kDwOffCtl + sizeof(DwCtl);
 
 struct DwBatchArgs {
   const mcf_dw_job_t* jobs;
-  const uint8_t* base[2];
-  long long tile_bytes[2];
+  const uint8_t* base[3];   // forward save record, backward save record, per-ray feature images
+  long long tile_bytes[3];
   float* staging;
   long long n_tiles;
 };
 
-__device__ __forceinline__ void dw_body(const mcf_dw_params_t& p, int nib, int cta, int n_cta);
+// second source of Q blocks (blocks >= split come from base + tile*tile_bytes + off)
+struct DwQ2 {
+  const uint8_t* base;
+  long long tile_bytes;
+  uint32_t off;
+  int split;
+};
+
+__device__ __forceinline__ void dw_body(const mcf_dw_params_t& p, const DwQ2& q2, int nib, int cta, int n_cta);
 
 __global__ void __launch_bounds__(kDwThreads, 1) k_dw(const __grid_constant__ mcf_dw_params_t p, int nib) {
-  dw_body(p, nib, blockIdx.x, gridDim.x);
+  DwQ2 q2 = {nullptr, 0, 0u, 1 << 20};
+  dw_body(p, q2, nib, blockIdx.x, gridDim.x);
 }
 
 // one launch for a list of jobs: blockIdx.y selects the job, blockIdx.x the (i-block, split) inside it
@@ -56,6 +65,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_batch(const __grid_constan
   const mcf_dw_job_t j = a.jobs[blockIdx.y];
   if (!j.enabled) return;
   mcf_dw_params_t p;
+  if (j.p_src < 0 || j.p_src > 2 || j.q_src < 0 || j.q_src > 2 || a.base[j.p_src] == nullptr || a.base[j.q_src] == nullptr) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(&g_mcf_device_error, 0xBAD50000u | blockIdx.y);
+    return;
+  }
   p.p_base = a.base[j.p_src]; p.p_tile_bytes = a.tile_bytes[j.p_src]; p.p_off = j.p_off; p.p_cols = j.p_cols;
   p.q_base = a.base[j.q_src]; p.q_tile_bytes = a.tile_bytes[j.q_src]; p.q_off = j.q_off; p.q_cols = j.q_cols;
   p.out = a.staging + j.st_off; p.ld_out = j.ld; p.n_i = j.n_i; p.n_j = j.n_j;
@@ -65,10 +78,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_batch(const __grid_constan
   int n_cta = (int)gridDim.x - ((int)gridDim.x % nib);   // CTAs of this job that take part
   if ((long long)(n_cta / nib) > a.n_tiles) n_cta = (int)a.n_tiles * nib;
   if ((int)blockIdx.x >= n_cta) return;
-  dw_body(p, nib, blockIdx.x, n_cta);
+  DwQ2 q2 = {a.base[2], a.tile_bytes[2], j.q2_off, (j.q_split >= 0 && a.base[2] != nullptr) ? j.q_split : (1 << 20)};
+  dw_body(p, q2, nib, blockIdx.x, n_cta);
 }
 
-__device__ __forceinline__ void dw_body(const mcf_dw_params_t& p, int nib, int cta, int n_cta) {
+__device__ __forceinline__ void dw_body(const mcf_dw_params_t& p, const DwQ2& q2, int nib, int cta, int n_cta) {
   extern __shared__ __align__(1024) uint8_t smem[];
   DwCtl& ctl = *reinterpret_cast<DwCtl*>(smem + kDwOffCtl);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -118,6 +132,7 @@ __device__ __forceinline__ void dw_body(const mcf_dw_params_t& p, int nib, int c
       for (long long t = split; t < p.n_tiles; t += nsplit) {
         const uint8_t* psrc = pb + t * p.p_tile_bytes + p.p_off + (uint32_t)ib * 2u * kBlkD;
         const uint8_t* qsrc = qb + t * p.q_tile_bytes + p.q_off;
+        const uint8_t* q2src = q2.base ? q2.base + t * q2.tile_bytes + q2.off : nullptr;
         for (uint32_t half = 0; half < 2; ++half) {
           mbar_wait(&ctl.empty[stage], phase ^ 1u, 0x500u | stage);
           // producer 0 posts the stage's byte count; the others' complete_tx may land first (the phase cannot
@@ -125,7 +140,9 @@ __device__ __forceinline__ void dw_body(const mcf_dw_params_t& p, int nib, int c
           if (me == 0) mbar_arrive_expect_tx(&ctl.full[stage], (2 + q_blocks) * kHalf);
           uint8_t* dst = smem + stage * kStageBytes;
           for (uint32_t b = me; b < 2 + q_blocks; b += kDwProducers) {
-            const uint8_t* src = b < 2 ? psrc + b * kBlkD : qsrc + (b - 2) * kBlkD;
+            const uint8_t* src = b < 2 ? psrc + b * kBlkD
+                                 : ((int)(b - 2) < q2.split ? qsrc + (b - 2) * kBlkD
+                                                            : q2src + (b - 2 - (uint32_t)q2.split) * kBlkD);
             bulk_g2s(dst + b * kHalf, src + half * kHalf, kHalf, &ctl.full[stage]);
           }
           if (++stage == kDwStages) { stage = 0; phase ^= 1u; }
@@ -202,11 +219,47 @@ __device__ __forceinline__ void dw_body(const mcf_dw_params_t& p, int nib, int c
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// per-ray feature columns -> bf16 tile images (thread = row, 8 x 16 B per row)
+__global__ void k_rayfeat_image(const float* __restrict__ rayfeat, int stride, int dim, long long n_rows,
+                                int rows_per_ray, uint8_t* __restrict__ out) {
+  const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // padded row index (tile * 128 + row)
+  const long long n_pad = (n_rows + MCF_TILE_ROWS - 1) / MCF_TILE_ROWS * MCF_TILE_ROWS;
+  if (m >= n_pad) return;
+  const bool valid = m < n_rows;
+  const float* rf = rayfeat + (valid ? m / rows_per_ray : 0) * stride;
+  uint8_t* blk = out + (m / MCF_TILE_ROWS) * (long long)MCF_BLOCK_BYTES;
+  const uint32_t row = (uint32_t)(m % MCF_TILE_ROWS);
+  for (int c8 = 0; c8 < 8; ++c8) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+      f[j] = (valid && c < dim) ? __ldg(rf + c) : 0.f;
+    }
+    uint4 v;
+    v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+    v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(blk + sw128_off(row, c8)) = v;
+  }
+}
+
 }  // namespace mcf
+
+extern "C" int mcf_rayfeat_image(const float* rayfeat, int rayfeat_stride, int rayfeat_dim, long long n_rows,
+                                 int rows_per_ray, void* out, cudaStream_t stream) {
+  if (n_rows <= 0) return 0;
+  if (!rayfeat || !out || rows_per_ray <= 0 || rayfeat_dim < 0 || rayfeat_dim > 64) return MCF_ERR_BAD_ARG;
+  const long long n_pad = (n_rows + MCF_TILE_ROWS - 1) / MCF_TILE_ROWS * MCF_TILE_ROWS;
+  mcf::k_rayfeat_image<<<(unsigned)(n_pad / 128), 128, 0, stream>>>(rayfeat, rayfeat_stride, rayfeat_dim, n_rows,
+                                                                   rows_per_ray, reinterpret_cast<uint8_t*>(out));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
 
 extern "C" int mcf_dw_gemm_batch(const mcf_dw_job_t* jobs_dev, int n_jobs, const void* fwd_save,
                                  long long fwd_tile_bytes, const void* bwd_save, long long bwd_tile_bytes,
-                                 float* staging, long long n_tiles, int ctas_per_job, cudaStream_t stream) {
+                                 const void* aux, long long aux_tile_bytes, float* staging, long long n_tiles,
+                                 int ctas_per_job, cudaStream_t stream) {
   if (n_jobs <= 0 || n_tiles <= 0) return 0;
   if (ctas_per_job < 2) return MCF_ERR_BAD_ARG;
   mcf::DwBatchArgs a;
@@ -215,6 +268,8 @@ extern "C" int mcf_dw_gemm_batch(const mcf_dw_job_t* jobs_dev, int n_jobs, const
   a.base[1] = reinterpret_cast<const uint8_t*>(bwd_save);
   a.tile_bytes[0] = fwd_tile_bytes;
   a.tile_bytes[1] = bwd_tile_bytes;
+  a.base[2] = reinterpret_cast<const uint8_t*>(aux);
+  a.tile_bytes[2] = aux_tile_bytes;
   a.staging = staging;
   a.n_tiles = n_tiles;
   cudaError_t e = cudaFuncSetAttribute(mcf::k_dw_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mcf::kDwSmem);

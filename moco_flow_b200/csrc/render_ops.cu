@@ -185,7 +185,9 @@ __device__ __forceinline__ float density_grad(float raw, int act) {
   return e / (e + 1.0f);
 }
 
-// sigma at sigma[m*sigma_stride], rgb (optional) at rgb[m*rgb_stride + 0..2]
+// sigma at sigma[m*sigma_stride], rgb (optional) at rgb[m*rgb_stride + 0..2].  kPacked: the two point into one
+// [M][4] = [r,g,b,sigma] array (what NeRF.forward returns, models/nerf.py:101) -> one 16-byte load per sample.
+template <bool kPacked>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_composite_fwd(const float* __restrict__ sigma, int sigma_stride, const float* __restrict__ rgb, int rgb_stride,
                 const float* __restrict__ z, const float* __restrict__ dirs, int dir_stride,
@@ -203,10 +205,24 @@ k_composite_fwd(const float* __restrict__ sigma, int sigma_stride, const float* 
     int i = c + lane;
     bool ok = i < S;
     float zi = ok ? z[base + i] : 0.f;
-    float zn = (i + 1 < S) ? z[base + i + 1] : 0.f;
+    // z[i+1]: the neighbour lane's value; the last lane of a chunk reads the next chunk's first element
+    float zn = __shfl_down_sync(kFull, zi, 1);
+    if (lane == 31) zn = (i + 1 < S) ? z[base + i + 1] : 0.f;
     float delta = (i + 1 < S) ? (zn - zi) : 1e10f;  // rendering.py:158-160
     delta = delta * dn;
-    float raw = ok ? sigma[(base + i) * sigma_stride] : 0.f;
+    float raw = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    if (kPacked) {
+      if (ok) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(rgb) + base + i);
+        c0 = v.x; c1 = v.y; c2 = v.z; raw = v.w;
+      }
+    } else if (ok) {
+      raw = sigma[(base + i) * sigma_stride];
+      if (rgb) {
+        const float* cc = rgb + (base + i) * rgb_stride;
+        c0 = cc[0]; c1 = cc[1]; c2 = cc[2];
+      }
+    }
     if (noise && ok) raw = raw + noise[base + i] * noise_std;  // rendering.py:166,170
     float alpha = ok ? (1.0f - expf(-delta * density(raw, act))) : 0.f;
     float q = ok ? (1.0f - alpha + 1e-10f) : 1.0f;  // rendering.py:177
@@ -222,10 +238,9 @@ k_composite_fwd(const float* __restrict__ sigma, int sigma_stride, const float* 
       sw += w;
       sd += w * zi;
       if (rgb) {
-        const float* cc = rgb + (base + i) * rgb_stride;
-        sr += w * cc[0];
-        sg += w * cc[1];
-        sb += w * cc[2];
+        sr += w * c0;
+        sg += w * c1;
+        sb += w * c2;
       }
     }
   }
@@ -255,6 +270,8 @@ k_composite_fwd(const float* __restrict__ sigma, int sigma_stride, const float* 
 
 // Analytic backward (recomputes alpha/T; per-warp smem scratch holds e=exp(-delta*dens), T, delta).
 // d_sigma written at d_sigma[m*ds_stride]; d_rgb (optional) at d_rgb[m*drgb_stride+0..2].
+// kPacked: inputs and gradients are [M][4] = [r,g,b,sigma] arrays -> one 16-byte load and one 16-byte store per sample.
+template <bool kPacked>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_composite_bwd(const float* __restrict__ sigma, int sigma_stride, const float* __restrict__ rgb, int rgb_stride,
                 const float* __restrict__ z, const float* __restrict__ dirs, int dir_stride,
@@ -277,7 +294,8 @@ k_composite_bwd(const float* __restrict__ sigma, int sigma_stride, const float* 
     int i = c + lane;
     bool ok = i < S;
     float zi = ok ? z[base + i] : 0.f;
-    float zn = (i + 1 < S) ? z[base + i + 1] : 0.f;
+    float zn = __shfl_down_sync(kFull, zi, 1);
+    if (lane == 31) zn = (i + 1 < S) ? z[base + i + 1] : 0.f;
     float delta = ((i + 1 < S) ? (zn - zi) : 1e10f) * dn;
     float raw = ok ? sigma[(base + i) * sigma_stride] : 0.f;
     if (noise && ok) raw = raw + noise[base + i] * noise_std;
@@ -317,15 +335,22 @@ k_composite_bwd(const float* __restrict__ sigma, int sigma_stride, const float* 
     float alpha = 1.0f - e;
     float w = alpha * T;
     float g = 0.f;
-    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, raw = 0.f;
     if (ok) {
       g = go + gd * z[base + i];
-      if (rgb) {
-        const float* cc = rgb + (base + i) * rgb_stride;
-        c0 = cc[0];
-        c1 = cc[1];
-        c2 = cc[2];
+      if (kPacked) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(rgb) + base + i);
+        c0 = v.x; c1 = v.y; c2 = v.z; raw = v.w;
         g += gr * (c0 - br) + gg * (c1 - bgc) + gb * (c2 - bb);
+      } else {
+        raw = sigma[(base + i) * sigma_stride];
+        if (rgb) {
+          const float* cc = rgb + (base + i) * rgb_stride;
+          c0 = cc[0];
+          c1 = cc[1];
+          c2 = cc[2];
+          g += gr * (c0 - br) + gg * (c1 - bgc) + gb * (c2 - bb);
+        }
       }
       if (g_weights) g += g_weights[base + i];
     }
@@ -342,15 +367,19 @@ k_composite_bwd(const float* __restrict__ sigma, int sigma_stride, const float* 
     if (ok) {
       float q = 1.0f - alpha + 1e-10f;
       float dalpha = g * T - after / q;  // cumprod backward (division form, as autograd)
-      float raw = sigma[(base + i) * sigma_stride];
       if (noise) raw = raw + noise[base + i] * noise_std;
       float ddens = dalpha * (delta * e);
-      d_sigma[(base + i) * ds_stride] = ddens * density_grad(raw, act);
-      if (d_rgb) {
-        float* o = d_rgb + (base + i) * drgb_stride;
-        o[0] = w * gr;
-        o[1] = w * gg;
-        o[2] = w * gb;
+      const float ds = ddens * density_grad(raw, act);
+      if (kPacked) {
+        reinterpret_cast<float4*>(d_rgb)[base + i] = make_float4(w * gr, w * gg, w * gb, ds);
+      } else {
+        d_sigma[(base + i) * ds_stride] = ds;
+        if (d_rgb) {
+          float* o = d_rgb + (base + i) * drgb_stride;
+          o[0] = w * gr;
+          o[1] = w * gg;
+          o[2] = w * gb;
+        }
       }
     }
   }
@@ -359,21 +388,31 @@ k_composite_bwd(const float* __restrict__ sigma, int sigma_stride, const float* 
 // -------------------------------------------------------------------------------------------------
 // sample_pdf (+ optional sort-merge with the coarse depths)
 // -------------------------------------------------------------------------------------------------
-// Per warp smem: cdf[nb+1] | bins[nb+1] | sort buffer [npow2]
+// One warp per ray.  Per-warp smem: cdf[nb+1] | bins[nb+1] | sorted samples [32*kEPL] | coarse z [n_coarse] |
+// merged [n_coarse + n_imp].
+// The merge with the coarse depths (rendering.py:326: sort(cat(z, samples))) does not sort 2S values: the fine samples
+// are sorted in registers (bitonic network over 32*kEPL values: shuffles for partner distances < 32, register
+// exchanges above), the coarse depths are already sorted, and every value's output position is its own rank plus its
+// rank in the other list (binary search; ties put the coarse value first, so the positions are a permutation).
+// Values are copied, never recomputed: the result equals torch.sort of the concatenation bit for bit.
+template <int kEPL>   // fine samples per lane: n_imp <= 32 * kEPL
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_sample_pdf(const float* __restrict__ bins, int bins_stride, int bins_are_z, const float* __restrict__ wts,
              int w_stride, const float* __restrict__ cdf_in, int cdf_stride, const float* __restrict__ u, int u_stride,
              float eps, int R, int nb, int n_imp, const float* __restrict__ z_coarse, int zc_stride, int n_coarse,
-             int npow2, float* __restrict__ samples, int* __restrict__ inds_out, float* __restrict__ cdf_out,
+             float* __restrict__ samples, int* __restrict__ inds_out, float* __restrict__ cdf_out,
              float* __restrict__ z_merged) {
   extern __shared__ float scratch[];
-  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  int r = blockIdx.x * kWarpsPerBlock + wib;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int r = blockIdx.x * kWarpsPerBlock + wib;
   if (r >= R) return;
-  int per_warp = 2 * (nb + 1) + npow2;
+  const int n_tot = n_coarse + n_imp;
+  const int per_warp = 2 * (nb + 1) + (z_merged ? 32 * kEPL + n_coarse + n_tot : 0);
   float* s_cdf = scratch + (size_t)wib * per_warp;
   float* s_bin = s_cdf + (nb + 1);
-  float* s_sort = s_bin + (nb + 1);
+  float* s_srt = s_bin + (nb + 1);
+  float* s_zc = s_srt + 32 * kEPL;
+  float* s_out = s_zc + n_coarse;
 
   // bins: given, or mid-points of the coarse depths (rendering.py:321)
   const float* brow = bins + (long long)r * bins_stride;
@@ -404,6 +443,10 @@ k_sample_pdf(const float* __restrict__ bins, int bins_stride, int bins_are_z, co
       run += __shfl_sync(kFull, incl, 31);
     }
   }
+  if (z_merged) {
+    const float* zc = z_coarse + (long long)r * zc_stride;
+    for (int j = lane; j < n_coarse; j += 32) s_zc[j] = zc[j];
+  }
   __syncwarp();
   if (cdf_out) {
     float* co = cdf_out + (long long)r * (nb + 1);
@@ -411,50 +454,92 @@ k_sample_pdf(const float* __restrict__ bins, int bins_stride, int bins_are_z, co
   }
 
   const float* urow = u + (long long)r * u_stride;
-  for (int k = lane; k < n_imp; k += 32) {
-    float uk = urow[k];
-    // searchsorted(cdf, u, right=True): first index with cdf[idx] > u, in [0, nb+1]   (:33)
-    int lo = 0, hi = nb + 1;
-    while (lo < hi) {
-      int mid = (lo + hi) >> 1;
-      if (s_cdf[mid] <= uk) lo = mid + 1; else hi = mid;
+  float v[kEPL];   // element e = q * 32 + lane
+#pragma unroll
+  for (int q = 0; q < kEPL; ++q) {
+    const int k = q * 32 + lane;
+    v[q] = CUDART_INF_F;
+    if (k < n_imp) {
+      float uk = urow[k];
+      // searchsorted(cdf, u, right=True): first index with cdf[idx] > u, in [0, nb+1]   (:33)
+      int lo = 0, hi = nb + 1;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (s_cdf[mid] <= uk) lo = mid + 1; else hi = mid;
+      }
+      int below = max(lo - 1, 0), above = min(lo, nb);  // :34-35
+      float c0 = s_cdf[below], c1 = s_cdf[above];
+      float b0 = s_bin[below], b1 = s_bin[above];
+      float denom = c1 - c0;
+      if (denom < eps) denom = 1.0f;  // :41-42
+      float sv = b0 + (uk - c0) / denom * (b1 - b0);  // :45
+      if (samples) samples[(long long)r * n_imp + k] = sv;
+      if (inds_out) inds_out[(long long)r * n_imp + k] = lo;
+      v[q] = sv;
     }
-    int below = max(lo - 1, 0), above = min(lo, nb);  // :34-35
-    float c0 = s_cdf[below], c1 = s_cdf[above];
-    float b0 = s_bin[below], b1 = s_bin[above];
-    float denom = c1 - c0;
-    if (denom < eps) denom = 1.0f;  // :41-42
-    float s = b0 + (uk - c0) / denom * (b1 - b0);  // :45
-    if (samples) samples[(long long)r * n_imp + k] = s;
-    if (inds_out) inds_out[(long long)r * n_imp + k] = lo;
-    if (z_merged) s_sort[n_coarse + k] = s;
   }
   if (!z_merged) return;
 
-  // sort(cat(z_coarse, samples))  (rendering.py:326): in-warp bitonic sort in shared memory
-  const float* zc = z_coarse + (long long)r * zc_stride;
-  for (int j = lane; j < n_coarse; j += 32) s_sort[j] = zc[j];
-  int n_tot = n_coarse + n_imp;
-  for (int j = n_tot + lane; j < npow2; j += 32) s_sort[j] = CUDART_INF_F;
-  __syncwarp();
-  for (int k = 2; k <= npow2; k <<= 1) {
+  // ---- bitonic sort of the 32*kEPL fine samples (padding = +inf) in registers ----
+#pragma unroll
+  for (int k = 2; k <= 32 * kEPL; k <<= 1) {
+#pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = lane; t < npow2; t += 32) {
-        int p = t ^ j;
-        if (p > t) {
-          float a = s_sort[t], b = s_sort[p];
-          bool up = (t & k) == 0;
-          if ((a > b) == up) {
-            s_sort[t] = b;
-            s_sort[p] = a;
+      if (j >= 32) {
+        const int dq = j >> 5;
+#pragma unroll
+        for (int q = 0; q < kEPL; ++q) {
+          if ((q & dq) == 0) {   // element (q, lane) vs (q + dq, lane); ascending block iff (e & k) == 0
+            const bool up = (((q * 32) & k) == 0);   // k >= 64 here: bit of q only
+            const float a = v[q], b = v[q + dq];
+            const float lo = fminf(a, b), hi = fmaxf(a, b);
+            v[q] = up ? lo : hi;
+            v[q + dq] = up ? hi : lo;
           }
         }
+      } else {
+#pragma unroll
+        for (int q = 0; q < kEPL; ++q) {
+          const int e = q * 32 + lane;
+          const float other = __shfl_xor_sync(kFull, v[q], j);
+          const bool up = (e & k) == 0;
+          const bool lower = (lane & j) == 0;           // this lane holds the smaller index of the pair
+          const float lo = fminf(v[q], other), hi = fmaxf(v[q], other);
+          v[q] = (lower == up) ? lo : hi;
+        }
       }
-      __syncwarp();
     }
   }
+#pragma unroll
+  for (int q = 0; q < kEPL; ++q) s_srt[q * 32 + lane] = v[q];
+  __syncwarp();
+
+  // ---- rank merge ----
+#pragma unroll
+  for (int q = 0; q < kEPL; ++q) {
+    const int e = q * 32 + lane;
+    if (e < n_imp) {   // position = own rank + #coarse <= value
+      const float x = v[q];
+      int lo = 0, hi = n_coarse;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (s_zc[mid] <= x) lo = mid + 1; else hi = mid;
+      }
+      s_out[e + lo] = x;
+    }
+  }
+  for (int j = lane; j < n_coarse; j += 32) {   // position = own rank + #samples < value
+    const float x = s_zc[j];
+    int lo = 0, hi = n_imp;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (s_srt[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    s_out[j + lo] = x;
+  }
+  __syncwarp();
   float* zo = z_merged + (long long)r * n_tot;
-  for (int j = lane; j < n_tot; j += 32) zo[j] = s_sort[j];
+  for (int j = lane; j < n_tot; j += 32) zo[j] = s_out[j];
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -618,9 +703,17 @@ int mcf_composite_fwd(const float* sigma, int sigma_stride, const float* rgb, in
                       float* depth_out, float* opacity_out, cudaStream_t stream) {
   if (activation != MCF_ACT_RELU && activation != MCF_ACT_SOFTPLUS) return MCF_ERR_BAD_ARG;
   if (n_rays <= 0 || n_samples <= 0) return 0;
-  k_composite_fwd<<<grid_for_warps(n_rays), kWarpsPerBlock * 32, 0, stream>>>(
-      sigma, sigma_stride, rgb, rgb_stride, z, dirs, dir_stride, noise, noise_std, background, activation, n_rays,
-      n_samples, weights, alphas, rgb_out, depth_out, opacity_out);
+  // [r,g,b,sigma] rows: 16-byte vector path
+  const bool packed = rgb != nullptr && sigma == rgb + 3 && sigma_stride == 4 && rgb_stride == 4 &&
+                      (reinterpret_cast<uintptr_t>(rgb) & 15u) == 0;
+  if (packed)
+    k_composite_fwd<true><<<grid_for_warps(n_rays), kWarpsPerBlock * 32, 0, stream>>>(
+        sigma, sigma_stride, rgb, rgb_stride, z, dirs, dir_stride, noise, noise_std, background, activation, n_rays,
+        n_samples, weights, alphas, rgb_out, depth_out, opacity_out);
+  else
+    k_composite_fwd<false><<<grid_for_warps(n_rays), kWarpsPerBlock * 32, 0, stream>>>(
+        sigma, sigma_stride, rgb, rgb_stride, z, dirs, dir_stride, noise, noise_std, background, activation, n_rays,
+        n_samples, weights, alphas, rgb_out, depth_out, opacity_out);
   return check_launch();
 }
 
@@ -633,13 +726,22 @@ int mcf_composite_bwd(const float* sigma, int sigma_stride, const float* rgb, in
   if (n_rays <= 0 || n_samples <= 0) return 0;
   size_t smem = (size_t)kWarpsPerBlock * 3 * n_samples * sizeof(float);
   if (smem > 200 * 1024) return MCF_ERR_UNSUPPORTED;
+  const bool packed = rgb != nullptr && d_rgb != nullptr && sigma == rgb + 3 && d_sigma == d_rgb + 3 &&
+                      sigma_stride == 4 && rgb_stride == 4 && d_sigma_stride == 4 && d_rgb_stride == 4 &&
+                      ((reinterpret_cast<uintptr_t>(rgb) | reinterpret_cast<uintptr_t>(d_rgb)) & 15u) == 0;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_composite_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = packed ? cudaFuncSetAttribute(k_composite_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(k_composite_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  k_composite_bwd<<<grid_for_warps(n_rays), kWarpsPerBlock * 32, smem, stream>>>(
-      sigma, sigma_stride, rgb, rgb_stride, z, dirs, dir_stride, noise, noise_std, background, activation, n_rays,
-      n_samples, g_rgb, g_depth, g_opacity, g_weights, d_sigma, d_sigma_stride, d_rgb, d_rgb_stride);
+  if (packed)
+    k_composite_bwd<true><<<grid_for_warps(n_rays), kWarpsPerBlock * 32, smem, stream>>>(
+        sigma, sigma_stride, rgb, rgb_stride, z, dirs, dir_stride, noise, noise_std, background, activation, n_rays,
+        n_samples, g_rgb, g_depth, g_opacity, g_weights, d_sigma, d_sigma_stride, d_rgb, d_rgb_stride);
+  else
+    k_composite_bwd<false><<<grid_for_warps(n_rays), kWarpsPerBlock * 32, smem, stream>>>(
+        sigma, sigma_stride, rgb, rgb_stride, z, dirs, dir_stride, noise, noise_std, background, activation, n_rays,
+        n_samples, g_rgb, g_depth, g_opacity, g_weights, d_sigma, d_sigma_stride, d_rgb, d_rgb_stride);
   return check_launch();
 }
 
@@ -649,21 +751,26 @@ int mcf_sample_pdf(const float* bins, int bins_stride, int bins_are_z, const flo
                    float* cdf_out, float* z_merged, cudaStream_t stream) {
   if (n_rays <= 0 || n_importance <= 0) return 0;
   if (n_bins < 1 || !u || (!weights && !cdf_in)) return MCF_ERR_BAD_ARG;
-  int npow2 = 0;
-  if (z_merged) {
-    if (!z_coarse) return MCF_ERR_BAD_ARG;
-    npow2 = 1;
-    while (npow2 < n_coarse + n_importance) npow2 <<= 1;
-  }
-  size_t smem = (size_t)kWarpsPerBlock * (2 * (n_bins + 1) + npow2) * sizeof(float);
+  if (z_merged && !z_coarse) return MCF_ERR_BAD_ARG;
+  if (n_importance > 256) return MCF_ERR_UNSUPPORTED;
+  const int epl = n_importance <= 64 ? 2 : (n_importance <= 128 ? 4 : 8);
+  size_t per_warp = 2 * (size_t)(n_bins + 1) + (z_merged ? (size_t)32 * epl + n_coarse + n_coarse + n_importance : 0);
+  size_t smem = (size_t)kWarpsPerBlock * per_warp * sizeof(float);
   if (smem > 200 * 1024) return MCF_ERR_UNSUPPORTED;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_sample_pdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-  }
-  k_sample_pdf<<<grid_for_warps(n_rays), kWarpsPerBlock * 32, smem, stream>>>(
-      bins, bins_stride, bins_are_z, weights, w_stride, cdf_in, cdf_stride, u, u_stride, eps, n_rays, n_bins,
-      n_importance, z_coarse, zc_stride, n_coarse, npow2, samples, inds_out, cdf_out, z_merged);
+#define MCF_SPDF(E_)                                                                                                  \
+  do {                                                                                                                \
+    if (smem > 48 * 1024) {                                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(k_sample_pdf<E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return (int)e;                                                                            \
+    }                                                                                                                 \
+    k_sample_pdf<E_><<<grid_for_warps(n_rays), kWarpsPerBlock * 32, smem, stream>>>(                                  \
+        bins, bins_stride, bins_are_z, weights, w_stride, cdf_in, cdf_stride, u, u_stride, eps, n_rays, n_bins,       \
+        n_importance, z_coarse, zc_stride, n_coarse, samples, inds_out, cdf_out, z_merged);                           \
+  } while (0)
+  if (epl == 2) MCF_SPDF(2);
+  else if (epl == 4) MCF_SPDF(4);
+  else MCF_SPDF(8);
+#undef MCF_SPDF
   return check_launch();
 }
 

@@ -410,6 +410,7 @@ def chain_params(pp: PackedPlan, n_rows: int, rows_per_ray: int, n_rays: int) ->
     cp.out_stride, cp.sigma_col = 4, 3
     cp.cta_pair = CTA_PAIR if pp.plan.width == 256 else 0
     cp.program_kind = pp.plan.kind
+    cp.wpack_bytes, cp.resident = pp.plan.wpack_bytes, int(pp.plan.resident)
     return cp
 
 

@@ -22,6 +22,10 @@ from . import _lib as L
 
 BLK = L.BLOCK_BYTES
 FUSE_N256 = os.environ.get("MCF_FUSE_N256", "1") != "0"
+# NoF programs (W = 128, <= 144 KB of packed weights) run on the resident-weight kernel: weights copied into shared
+# memory once per CTA, no per-tile weight stream.  MCF_NOF_RESIDENT=0 builds the streamed (ring) programs instead.
+NOF_RESIDENT = os.environ.get("MCF_NOF_RESIDENT", "1") != "0"
+RES_BYTES = 147456
 
 
 def _ceil(a: int, b: int) -> int:
@@ -42,6 +46,7 @@ class Plan:
     offsets: Dict[str, int] = field(default_factory=dict)   # named save / mask / const offsets
     n_raybias: int = 0
     kind: int = 0          # 0: NeRF program, 1: NoF program (selects the kernel instantiation)
+    resident: bool = False  # built for the resident-weight kernel (mcf_chain_params_t.resident)
 
 
 class _Builder:
@@ -109,14 +114,15 @@ class _Builder:
         self.mask_words += _ceil(n_cols, 32) * 128
         return off
 
-    def finish(self, n_raybias: int = 0, kind: int = 0) -> Plan:
+    def finish(self, n_raybias: int = 0, kind: int = 0, resident: bool = False) -> Plan:
         self.chunks = [tuple(c) for c in self.chunks]
         assert len(self.chunks) <= 128 and len(self.rounds) <= 24 and len(self.names) <= 32, \
             (len(self.chunks), len(self.rounds), len(self.names))
+        assert not resident or self.wbytes <= RES_BYTES
         return Plan(self.width, list(self.names),
                     np.array(self.pack, dtype=L.PACK_DT), np.array(self.chunks, dtype=L.CHUNK_DT),
                     np.array(self.rounds, dtype=L.ROUND_DT), self.wbytes, max(self.nconst, 4),
-                    self.save_bytes, self.mask_words, dict(self.offsets), n_raybias, kind)
+                    self.save_bytes, self.mask_words, dict(self.offsets), n_raybias, kind, resident)
 
 
 def _check_common(W: int, cx: int) -> None:
@@ -148,7 +154,6 @@ def nerf_forward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: 
     nkb, NH = W // 64, W // 128
     if training:
         b.save_slot("x0", 1)
-        b.save_slot("extra", 1)
     for i in range(D):
         wname, bname = f"xyz_encoding_{i+1}.0.weight", f"xyz_encoding_{i+1}.0.bias"
         ld = cx if i == 0 else (W + cx if i in skips else W)
@@ -189,31 +194,59 @@ def nerf_forward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: 
     return b.finish(n_raybias=1 if (extra_dim > 0 and not sigma_only) else 0)
 
 
+def nof_resident_ok(D: int, W: int, cx: int, skips: Sequence[int]) -> bool:
+    """Whether a NoF of these shapes runs on the resident-weight kernel: W = 128, at most one skip layer (its x0 part
+    is precomputed into the second half of the slot's accumulator in round 0), forward and backward streams <= 144 KB."""
+    if not NOF_RESIDENT or W != 128:
+        return False
+    n_skip = len([i for i in range(1, D) if i in skips])
+    if n_skip > 1:
+        return False
+    fwd = BLK * (1 + n_skip) + (D - 1) * 2 * BLK + 2 * 2048
+    bwd = BLK + (D - 1) * 2 * BLK + (1 + n_skip) * 2 * (BLK // 2)
+    return max(fwd, bwd) <= RES_BYTES
+
+
 def nof_forward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: int, use_quat: bool,
                      training: bool) -> Plan:
     """models/nof.py:55-85 as a chain program.  The per-ray index-embedding columns of layer 1 and of
-    the skip layers are folded into per-ray bias vectors (mcf_ray_bias), in list order."""
+    the skip layers are folded into per-ray bias vectors (mcf_ray_bias), in list order.
+
+    Resident-weight form (nof_resident_ok): the first-layer operand x0 shares the activation buffer, so it is gone
+    after round 0; the skip layer's x0 part (cat([inputs, h]) @ W^T = inputs @ Wx^T + h @ Wh^T, models/nof.py:71-72)
+    is therefore issued in round 0 into accumulator columns [128, 256) and the skip round accumulates its h part on
+    top -- the same summation order as the streamed form, so the results are bit-identical."""
     _check_common(W, cx)
     b = _Builder(W)
     nkb, NH = W // 64, W // 128
+    resident = nof_resident_ok(D, W, cx, skips)
+    kx = _ceil(cx, 16)
     if training:
         b.save_slot("x0", 1)
-        b.save_slot("extra", 1)
     rb = 0
     for i in range(D):
         wname, bname = f"nof_encoding_{i+1}.0.weight", f"nof_encoding_{i+1}.0.bias"
         cin = cx + extra_dim
         ld = cin if i == 0 else (W + cin if i in skips else W)
         c0 = len(b.chunks)
+        is_skip = i in skips and i > 0
+        acc = 128 if (resident and is_skip) else 0
         for si, (abuf, kb, ks, col0, ncols) in enumerate(_trunk_sources(i, skips, cx, nkb, extra_dim)):
+            if resident and is_skip and abuf == 0:
+                continue        # issued in round 0 (below)
             for nh in range(NH):
                 img = b.image(wname, nh * 128, 128, col0, ncols, ld, False, 128)
-                b.chunk(img, abuf, kb, ks, 128, nh * 128, init=(si == 0))
+                b.chunk(img, abuf, kb, ks, 128, acc + nh * 128, init=(si == 0))
+        if resident and i == 0:
+            for j in range(1, D):
+                if j in skips:
+                    img = b.image(f"nof_encoding_{j+1}.0.weight", 0, 128, 0, cx, W + cin, False, 128)
+                    b.chunk(img, 0, 0, kx, 128, 128, init=True)
         folded = (i == 0 or i in skips) and extra_dim > 0
         boff = 0 if folded else b.const(bname, 0, 1, 0, W, W)
         save = b.save_slot(f"h{i+1}", nkb) if training else L.NONE
         mask = b.mask_slot(f"h{i+1}", W) if training else L.NONE
-        b.round(L.EPI_RELU, W, 0, c0, raybias=(rb if folded else -1), const_off=boff, save_off=save, mask_off=mask)
+        b.round(L.EPI_RELU, W, acc, c0, raybias=(rb if folded else -1), const_off=boff, save_off=save, mask_off=mask)
         if folded:
             rb += 1
     n_head = 9 if use_quat else 3
@@ -225,7 +258,7 @@ def nof_forward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: i
     b.round(L.EPI_NOF_HEAD, 16, 0, c0, const_off=boff)
     if rb > 4:
         raise ValueError("at most 4 folded layers (first + 3 skips) are supported")
-    return b.finish(n_raybias=rb, kind=1)
+    return b.finish(n_raybias=rb, kind=1, resident=resident)
 
 
 def folded_layers(D: int, skips: Sequence[int]) -> List[int]:
@@ -251,6 +284,8 @@ class GradJob:
     n_j: int
     colsum_off: int  # float offset in staging of colsum_p, or -1
     params: tuple    # parameter names this job feeds
+    q_split: int = -1  # leading 64-column Q blocks taken from q_src; the rest from the per-ray feature images
+    q2_off: int = 0
 
 
 @dataclass
@@ -285,12 +320,12 @@ class _GradBuilder:
         self.st += _ceil(n, 4) * 4
         return off
 
-    def job(self, P, Q, n_i, n_j, params, colsum=False) -> GradJob:
+    def job(self, P, Q, n_i, n_j, params, colsum=False, q_split=-1) -> GradJob:
         n_j4 = _ceil(n_j, 4) * 4
         ld = n_j4
         st = self.alloc(n_i * ld)
         cs = self.alloc(n_i) if colsum else -1
-        j = GradJob(P[0], P[1], P[2], Q[0], Q[1], Q[2], st, ld, n_i, n_j4, cs, tuple(params))
+        j = GradJob(P[0], P[1], P[2], Q[0], Q[1], Q[2], st, ld, n_i, n_j4, cs, tuple(params), q_split, 0)
         self.jobs.append(j)
         return j
 
@@ -337,9 +372,11 @@ def _bwd_trunk(b: _Builder, fwd: Plan, D: int, W: int, cx: int, skips, skip_extr
 def job_table(gp: "GradPlan", wanted: set) -> np.ndarray:
     """Device job table (mcf_dw_job_t) of a gradient plan; jobs feeding no wanted parameter are disabled."""
     rows = []
+    src = {"fwd": 0, "bwd": 1, "aux": 2}   # forward / backward save record, per-ray feature images (mcf_rayfeat_image)
     for j in gp.jobs:
-        rows.append((j.p_off, j.q_off, 0 if j.p_src == "fwd" else 1, 0 if j.q_src == "fwd" else 1, j.p_cols, j.q_cols,
-                     j.st_off, j.ld, j.n_i, j.n_j, j.colsum_off, int(any(n in wanted for n in j.params))))
+        rows.append((j.p_off, j.q_off, src[j.p_src], src[j.q_src], j.p_cols, j.q_cols,
+                     j.st_off, j.ld, j.n_i, j.n_j, j.colsum_off, int(any(n in wanted for n in j.params)),
+                     j.q_split, j.q2_off))
     return np.array(rows, dtype=L.DWJOB_DT)
 
 
@@ -389,7 +426,7 @@ def nof_backward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: 
         b.chunk(img, 1, 0, 1, 128, nh * 128, init=True)
     b.round(L.EPI_B_MASK, W, 0, c0, save_off=b.save_slot(f"dy{D}", nkb), mask_off=fwd.offsets[f"mask_h{D}"])
     _bwd_trunk(b, fwd, D, W, cx, tuple(skips), extra_dim, "nof_encoding", need_dx)
-    return b.finish(kind=1)
+    return b.finish(kind=1, resident=fwd.resident)
 
 
 def nerf_grad_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: int, shapes: Dict[str, tuple],
@@ -421,7 +458,7 @@ def nerf_grad_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: int
     g.scatter(j.st_off, j.ld, en, 0, 0, half, W)
     g.scatter(j.colsum_off, half, eb, 0, 0, 1, half)
     if extra_dim > 0:
-        j = g.job(B("dye", half), F("extra", 64), half, 64, (en,))
+        j = g.job(B("dye", half), ("aux", 0, 64), half, 64, (en,))
         g.scatter(j.st_off, j.ld, en, 0, W, half, extra_dim)
     j = g.job(F("he", half), B("dhead", 64), half, 4, ("rgb.0.weight",))
     g.scatter(j.st_off, j.ld, "rgb.0.weight", 0, 0, 3, half, transposed=True)
@@ -445,8 +482,8 @@ def nof_grad_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: int,
         is_skip = i in skips and i > 0
         first = True
         if i == 0 or is_skip:
-            # Q = [x0 block | per-ray feature block] (adjacent in the forward save record)
-            j = g.job(P, F("x0", 128), W, 128, (wn, bn), colsum=True)
+            # Q = [x0 block (forward save record) | per-ray feature block (shared images, mcf_rayfeat_image)]
+            j = g.job(P, F("x0", 128), W, 128, (wn, bn), colsum=True, q_split=1)
             g.scatter(j.st_off, j.ld, wn, 0, 0, W, cx)
             if extra_dim > 0:
                 g.scatter(j.st_off + 64, j.ld, wn, 0, cx, W, extra_dim)

@@ -64,7 +64,7 @@ def test_nerf_plan_shapes():
     so = P.nerf_forward_plan(8, 256, 63, (4,), 5, sigma_only=True, training=False)
     assert len(so.rounds) == 8 and len(so.chunks) == 60
     tr = P.nerf_forward_plan(8, 256, 63, (4,), 5, sigma_only=False, training=True)
-    assert tr.save_tile_bytes == (1 + 1 + 8 * 4 + 4 + 2) * 16384
+    assert tr.save_tile_bytes == (1 + 8 * 4 + 4 + 2) * 16384   # x0, h1..h8, feat, he (per-ray features: shared images)
     assert tr.mask_tile_words == 8 * 8 * 128 + 4 * 128
     # every chunk consumes columns that exist; first chunk of each accumulator region initialises it
     for r in pl.rounds:
@@ -142,7 +142,7 @@ def test_plans_carry_their_program_family():
     assert all(int(e) < 16 for e in nf.rounds["epi"]) and all(int(e) >= 16 for e in nb.rounds["epi"])
     assert int(of.rounds["epi"][-1]) == L.EPI_NOF_HEAD
     names = [f[0] for f in L.ChainParams._fields_]
-    assert names[-3:] == ["cta_pair", "program_kind", "pe_table"]
+    assert names[-5:] == ["cta_pair", "program_kind", "pe_table", "wpack_bytes", "resident"]
 
 
 def test_bench_reference_arm_contract():
