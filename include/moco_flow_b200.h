@@ -224,12 +224,21 @@ typedef struct {
    * schedule (trainer/trainer_moco_flow.py:280-305); values passed by pointer stay current when the launch is
    * replayed from a captured CUDA graph, values passed in this struct are frozen at capture. */
   const float* pe_table;
-  /* resident != 0 (width 128, NoF programs): the program was built for the resident-weight kernel -- the whole packed
-   * weight stream (wpack_bytes <= 144 KB) is copied into shared memory once per CTA instead of being streamed per
-   * tile, and the first-layer operand shares the activation buffer (the plan precomputes the skip layer's x0 part in
-   * round 0).  Plans of the two kinds are not interchangeable. */
+  /* resident != 0 (width 128, NoF programs): the whole packed weight stream (wpack_bytes <= 144 KB) is copied into
+   * shared memory once per CTA instead of being streamed per tile.
+   *   1: chain.cu's kernel with activations in shared memory; the first-layer operand shares the activation buffer
+   *      (the plan precomputes the skip layer's x0 part in round 0);
+   *   2: nof_chain.cu -- activations are the A operand in tensor memory (tcgen05.mma with A in TMEM, written by
+   *      tcgen05.st from the epilogue), 16 epilogue warps per CTA; plans keep x0 available for the skip layer.
+   * Plans of the three kinds (0, 1, 2) are not interchangeable. */
   uint32_t wpack_bytes;
   int32_t resident;
+  /* backward, NeRF programs: gradient w.r.t. already-embedded input rows (the reference feeds NoF outputs through
+   * Embedding into NeRF.forward(inputs), trainer/trainer_moco_flow.py:146-158,349-361): when non-NULL the dX rounds
+   * write d_dense[m*d_dense_stride + c], c < dense_cols, instead of applying the encoder's Jacobian. */
+  float* d_dense;
+  int32_t d_dense_stride;
+  int32_t reserved0;
 } mcf_chain_params_t;
 
 int mcf_chain_launch(const mcf_chain_params_t* params_host, cudaStream_t stream);

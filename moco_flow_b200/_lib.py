@@ -57,7 +57,7 @@ class ChainParams(C.Structure):
         ("d_xyz", _vp), ("d_head", _vp), ("rayfeat", _vp), ("rayfeat_stride", _i32), ("rayfeat_dim", _i32),
         ("extra_save_off", _u32), ("dhead_save_off", _u32), ("max_ctas", _i32),
         ("timing", _vp), ("cta_pair", _i32), ("program_kind", _i32), ("pe_table", _vp),
-        ("wpack_bytes", _u32), ("resident", _i32),
+        ("wpack_bytes", _u32), ("resident", _i32), ("d_dense", _vp), ("d_dense_stride", _i32), ("reserved0", _i32),
     ]
 
 

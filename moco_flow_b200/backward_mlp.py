@@ -169,6 +169,9 @@ class _NeRFFn(torch.autograd.Function):
         ctx.model, ctx.pe, ctx.names, ctx.M, ctx.S = model, pe, names, M, rows_per_ray
         ctx.dense_mode = dense is not None
         ctx.need_dx = xyz is not None and xyz.requires_grad
+        # reference call convention NeRF.forward(inputs) with inputs that carry grad (trainer_moco_flow.py:146-158)
+        ctx.need_ddense = dense is not None and dense.requires_grad
+        ctx.dense_shape = tuple(dense.shape) if dense is not None else None
         ctx.aux = rayfeat_images(rf, M, rows_per_ray) if rf is not None else None
         ctx.save_for_backward(save, masks, out)
         return out
@@ -180,7 +183,7 @@ class _NeRFFn(torch.autograd.Function):
         dev = out.device
         st = _train_state(model)
         fwd_plan = model._plan(False, True).plan
-        need_dx = bool(ctx.need_dx)
+        need_dx = bool(ctx.need_dx) or bool(ctx.need_ddense)
         if need_dx not in st.bwd:
             bplan = P.nerf_backward_plan(model.D, model.W, model.in_channels_xyz, tuple(model.skips),
                                          model._extra_dim(), need_dx, fwd_plan)
@@ -206,13 +209,23 @@ class _NeRFFn(torch.autograd.Function):
         cp.dhead_save_off = bplan.offsets["save_dhead"]
         d_head = torch.empty(M, 4, device=dev)
         cp.d_head = d_head.data_ptr()
-        d_xyz = None
-        if need_dx:
+        d_xyz = d_dense = None
+        if ctx.need_ddense:
+            d_dense = torch.zeros(ctx.dense_shape, device=dev)
+            cp.d_dense, cp.d_dense_stride, cp.dense_cols = d_dense.data_ptr(), d_dense.stride(0), model.in_channels_xyz
+        elif need_dx:
             d_xyz = torch.empty(M, 3, device=dev)
             cp.d_xyz = d_xyz.data_ptr()
             ops.set_pe(cp, ctx.pe, model.in_channels_xyz, dev)
         first = 2.0 * model.in_channels_xyz * model.W * (1 + len([s for s in model.skips if s > 0]))
         ops.launch_chain(cp, "nerf_bwd_dx", ops.linear_flops(model) - (0.0 if need_dx else first))
+        E = model._extra_dim()
+        if d_dense is not None and E > 0 and ctx.dense_shape[1] > model.in_channels_xyz:
+            # extra-feature columns of the input rows: d = dYe @ W_e[:, W:W+E], dYe read back from its saved bf16 image
+            dye = ops.image_rows(bsave, nt, bplan.save_tile_bytes, bplan.offsets["save_dye"], model.W // 2)[:M]
+            w_e = model.extra_encoding[0].weight.detach()[:, model.W:model.W + E]
+            ncol = min(E, ctx.dense_shape[1] - model.in_channels_xyz)
+            d_dense[:, model.in_channels_xyz:model.in_channels_xyz + ncol] = (dye @ w_e)[:, :ncol]
         needs = list(ctx.needs_input_grad[7:])
         wanted = {n for n, need in zip(ctx.names, needs) if need}
         pgrads = [None] * len(ctx.names)
@@ -222,12 +235,10 @@ class _NeRFFn(torch.autograd.Function):
                                   bplan.save_tile_bytes, nt, d_head, wanted, ctx.aux)
             if flat is not None:
                 pgrads = _param_grads(gp, flat, ctx.names, needs)
-        return (None, None, None, d_xyz, None, None, None, *pgrads)
+        return (None, None, None, d_xyz, d_dense, None, None, *pgrads)
 
 
 def nerf_autograd(model, xyz, pe, dense, ray_feat, rows_per_ray, sigma_only):
-    if dense is not None and dense.requires_grad:
-        raise NotImplementedError("gradients w.r.t. pre-embedded inputs are not provided; pass xyz + Embedding")
     names = [n for n, _ in model.named_parameters()]
     params = [p for _, p in model.named_parameters()]
     if sigma_only:

@@ -24,12 +24,14 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 UNITS = [
     ("render_ops.cu", ["-fmad=false"]),
     ("chain.cu", []),
+    ("nof_chain.cu", []),
     ("gemm_dw.cu", []),
     ("optim.cu", []),
     ("camera.cu", ["-fmad=false"]),
     ("correspondence.cu", ["-fmad=false"]),
 ]
-HEADERS = [os.path.join(CSRC, "ptx.cuh"), os.path.join(ROOT, "include", "moco_flow_b200.h")]
+HEADERS = [os.path.join(CSRC, "ptx.cuh"), os.path.join(CSRC, "nof_math.cuh"),
+           os.path.join(ROOT, "include", "moco_flow_b200.h")]
 
 
 def _nvcc() -> str:

@@ -1,7 +1,11 @@
 // Nearest SMPL vertex + per-vertex rigid transform of query points: the KNN(k=1) correspondence
 // sampling that feeds the flow networks' supervision, datasets/moco_flow_dataset.py:121-130 (knn_cuda's
 // KNN(k=1, transpose_mode=True) over ~6.9 K vertices, then trans[ind] @ [x, 1]).  Brute force with the vertices staged
-// through shared memory; one thread per query.  fp32, -fmad=false: d2 = (dx*dx + dy*dy) + dz*dz, first minimum wins.
+// through shared memory; one thread per query.  The squared distance is formed exactly as knn_cuda's
+// cuComputeDistanceGlobal does (knn_cuda/csrc/cuda/knn.cu inside docker/KNN_CUDA-0.2-py3-none-any.whl: tmp = ref - query,
+// ssd += tmp*tmp over x, y, z, contracted to FMAs by nvcc's default -fmad=true): d2 = fma(dz,dz, fma(dy,dy, dx*dx));
+// cuInsertionSort with k = 1 keeps the FIRST strict minimum; cuParallelSqrt takes sqrtf.  Indices and distances are
+// bit-identical to the reference kernel (tests/test_correspondence.py against oracle/_ref/libknn_cuda_ref.so).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -37,8 +41,8 @@ __global__ void __launch_bounds__(kKnnThreads) k_nearest_vertex(const float* __r
     if (live) {
 #pragma unroll 4
       for (int i = 0; i < n; ++i) {
-        const float dx = x - sx[i], dy = y - sy[i], dz = z - sz[i];
-        const float d2 = (dx * dx + dy * dy) + dz * dz;
+        const float dx = sx[i] - x, dy = sy[i] - y, dz = sz[i] - z;
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
         if (d2 < best) { best = d2; best_i = v0 + i; }
       }
     }

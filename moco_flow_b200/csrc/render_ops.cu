@@ -201,29 +201,43 @@ k_composite_fwd(const float* __restrict__ sigma, int sigma_stride, const float* 
   float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);  // rendering.py:164
   long long base = (long long)r * S;
   float carry = 1.0f, sw = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f;
+  // The chunks of a ray are a serial chain (the transmittance carry), so the loads of chunk c + 1 are issued before
+  // the scan of chunk c: two chunks of HBM requests in flight per warp.
+  struct In { float zi, zn31, raw, c0, c1, c2, ns; };
+  auto fetch = [&](int c) {
+    In t = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int i = c + lane;
+    if (i < S) {
+      t.zi = z[base + i];
+      if (lane == 31 && i + 1 < S) t.zn31 = z[base + i + 1];   // the next chunk's first depth
+      if (kPacked) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(rgb) + base + i);
+        t.c0 = v.x; t.c1 = v.y; t.c2 = v.z; t.raw = v.w;
+      } else {
+        t.raw = sigma[(base + i) * sigma_stride];
+        if (rgb) {
+          const float* cc = rgb + (base + i) * rgb_stride;
+          t.c0 = cc[0]; t.c1 = cc[1]; t.c2 = cc[2];
+        }
+      }
+      if (noise) t.ns = noise[base + i];
+    }
+    return t;
+  };
+  In nxt = fetch(0);
   for (int c = 0; c < S; c += 32) {
+    const In cur = nxt;
+    if (c + 32 < S) nxt = fetch(c + 32);
     int i = c + lane;
     bool ok = i < S;
-    float zi = ok ? z[base + i] : 0.f;
-    // z[i+1]: the neighbour lane's value; the last lane of a chunk reads the next chunk's first element
+    float zi = cur.zi;
+    // z[i+1]: the neighbour lane's value; the last lane of a chunk holds the next chunk's first element
     float zn = __shfl_down_sync(kFull, zi, 1);
-    if (lane == 31) zn = (i + 1 < S) ? z[base + i + 1] : 0.f;
+    if (lane == 31) zn = cur.zn31;
     float delta = (i + 1 < S) ? (zn - zi) : 1e10f;  // rendering.py:158-160
     delta = delta * dn;
-    float raw = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-    if (kPacked) {
-      if (ok) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(rgb) + base + i);
-        c0 = v.x; c1 = v.y; c2 = v.z; raw = v.w;
-      }
-    } else if (ok) {
-      raw = sigma[(base + i) * sigma_stride];
-      if (rgb) {
-        const float* cc = rgb + (base + i) * rgb_stride;
-        c0 = cc[0]; c1 = cc[1]; c2 = cc[2];
-      }
-    }
-    if (noise && ok) raw = raw + noise[base + i] * noise_std;  // rendering.py:166,170
+    float raw = cur.raw, c0 = cur.c0, c1 = cur.c1, c2 = cur.c2;
+    if (noise && ok) raw = raw + cur.ns * noise_std;  // rendering.py:166,170
     float alpha = ok ? (1.0f - expf(-delta * density(raw, act))) : 0.f;
     float q = ok ? (1.0f - alpha + 1e-10f) : 1.0f;  // rendering.py:177
     float incl = warp_incl_prod(q, lane);

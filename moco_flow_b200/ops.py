@@ -440,6 +440,20 @@ def launch_chain(cp: L.ChainParams, tag: str = "chain", flops_per_row: float = 0
         TIMING.setdefault(tag, []).append(buf)
 
 
+def image_rows(buf: torch.Tensor, n_tiles: int, tile_bytes: int, off: int, n_cols: int) -> torch.Tensor:
+    """A saved bf16 operand image ([n_tiles] records, blocks of [128 rows][64 cols], 16-byte chunk c of row r stored at
+    chunk c ^ (r & 7)) back as a row-major fp32 (n_tiles*128, n_cols) tensor.  Plumbing for rarely used gradient paths
+    (pre-embedded inputs); the hot paths consume the images on the tensor cores."""
+    nb = (n_cols + 63) // 64
+    rec = buf.view(n_tiles, tile_bytes)[:, off:off + nb * L.BLOCK_BYTES].contiguous()
+    x = rec.view(torch.bfloat16).view(n_tiles, nb, 128, 8, 8)            # [tile][block][row][stored chunk][8]
+    r = torch.arange(128, device=buf.device).view(128, 1)
+    c = torch.arange(8, device=buf.device).view(1, 8)
+    src = (c ^ (r & 7)).view(1, 1, 128, 8, 1).expand(n_tiles, nb, 128, 8, 8)
+    x = torch.gather(x, 3, src)                                          # logical chunk c <- stored chunk c ^ (r & 7)
+    return x.permute(0, 2, 1, 3, 4).reshape(n_tiles * 128, nb * 64)[:, :n_cols].float()
+
+
 def linear_flops(module) -> float:
     """Algorithmic FLOPs per row of a module's Linear layers (2*in*out, un-padded reference shapes)."""
     return float(sum(2 * m.in_features * m.out_features for m in module.modules() if isinstance(m, torch.nn.Linear)))

@@ -25,6 +25,9 @@ FUSE_N256 = os.environ.get("MCF_FUSE_N256", "1") != "0"
 # NoF programs (W = 128, <= 144 KB of packed weights) run on the resident-weight kernel: weights copied into shared
 # memory once per CTA, no per-tile weight stream.  MCF_NOF_RESIDENT=0 builds the streamed (ring) programs instead.
 NOF_RESIDENT = os.environ.get("MCF_NOF_RESIDENT", "1") != "0"
+# which resident kernel: "ts" = nof_chain.cu (activations in tensor memory, mcf_chain_params_t.resident = 2),
+# "smem" = chain.cu's resident variant (resident = 1)
+NOF_KERNEL = os.environ.get("MCF_NOF_KERNEL", "ts")
 RES_BYTES = 147456
 
 
@@ -46,7 +49,7 @@ class Plan:
     offsets: Dict[str, int] = field(default_factory=dict)   # named save / mask / const offsets
     n_raybias: int = 0
     kind: int = 0          # 0: NeRF program, 1: NoF program (selects the kernel instantiation)
-    resident: bool = False  # built for the resident-weight kernel (mcf_chain_params_t.resident)
+    resident: int = 0      # mcf_chain_params_t.resident: 0 streamed weights, 1 resident (smem activations), 2 TMEM-resident
 
 
 class _Builder:
@@ -114,7 +117,7 @@ class _Builder:
         self.mask_words += _ceil(n_cols, 32) * 128
         return off
 
-    def finish(self, n_raybias: int = 0, kind: int = 0, resident: bool = False) -> Plan:
+    def finish(self, n_raybias: int = 0, kind: int = 0, resident: int = 0) -> Plan:
         self.chunks = [tuple(c) for c in self.chunks]
         assert len(self.chunks) <= 128 and len(self.rounds) <= 24 and len(self.names) <= 32, \
             (len(self.chunks), len(self.rounds), len(self.names))
@@ -220,6 +223,9 @@ def nof_forward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: i
     b = _Builder(W)
     nkb, NH = W // 64, W // 128
     resident = nof_resident_ok(D, W, cx, skips)
+    if resident and NOF_KERNEL == "ts":
+        resident = 2          # x0 stays in tensor memory: the plain program (no round-0 precompute)
+    precompute = resident == 1
     kx = _ceil(cx, 16)
     if training:
         b.save_slot("x0", 1)
@@ -230,14 +236,14 @@ def nof_forward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: i
         ld = cin if i == 0 else (W + cin if i in skips else W)
         c0 = len(b.chunks)
         is_skip = i in skips and i > 0
-        acc = 128 if (resident and is_skip) else 0
+        acc = 128 if (precompute and is_skip) else 0
         for si, (abuf, kb, ks, col0, ncols) in enumerate(_trunk_sources(i, skips, cx, nkb, extra_dim)):
-            if resident and is_skip and abuf == 0:
+            if precompute and is_skip and abuf == 0:
                 continue        # issued in round 0 (below)
             for nh in range(NH):
                 img = b.image(wname, nh * 128, 128, col0, ncols, ld, False, 128)
                 b.chunk(img, abuf, kb, ks, 128, acc + nh * 128, init=(si == 0))
-        if resident and i == 0:
+        if precompute and i == 0:
             for j in range(1, D):
                 if j in skips:
                     img = b.image(f"nof_encoding_{j+1}.0.weight", 0, 128, 0, cx, W + cin, False, 128)
@@ -258,7 +264,7 @@ def nof_forward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: i
     b.round(L.EPI_NOF_HEAD, 16, 0, c0, const_off=boff)
     if rb > 4:
         raise ValueError("at most 4 folded layers (first + 3 skips) are supported")
-    return b.finish(n_raybias=rb, kind=1, resident=resident)
+    return b.finish(n_raybias=rb, kind=1, resident=int(resident))
 
 
 def folded_layers(D: int, skips: Sequence[int]) -> List[int]:

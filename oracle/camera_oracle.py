@@ -54,13 +54,37 @@ def canvas_scatter(background, rays_msk, rgb, depth, opacity):
     return img_raw, depth_raw
 
 
+def _fma32(a, b, c):
+    """float32 fused multiply-add: the product of two float32 is exact in float64; one rounding of the sum to float64
+    and one to float32 (a double rounding differs from a true fma only on exact float64 half-way cases)."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
 def nearest_vertex(verts, query, trans, thickness):
-    """datasets/moco_flow_dataset.py:121-130 with knn_cuda.KNN(k=1, transpose_mode=True) restated as a brute-force
-    argmin (knn_cuda is not installed and not vendored: parity of this piece is UNPINNED; the restatement follows its
-    documented contract -- Euclidean distance and index of the nearest reference point)."""
-    d2 = ((query[:, None, :] - verts[None, :, :]) ** 2).sum(-1)
-    best, ind = d2.min(dim=1)
-    dist = best.sqrt()
+    """datasets/moco_flow_dataset.py:121-130.  ``knn_cuda.KNN(k=1, transpose_mode=True)`` restated from its source,
+    which ships in the reference tree (docker/KNN_CUDA-0.2-py3-none-any.whl: knn_cuda/csrc/cuda/knn.cu):
+      cuComputeDistanceGlobal  tmp = ref - query per coordinate, ``ssd += tmp*tmp`` over x, y, z in that order (nvcc's
+                               default -fmad=true contracts each to an FMA; the first one adds to 0);
+      cuInsertionSort (k = 1)  keeps the first strict minimum over the reference index;
+      cuParallelSqrt           sqrt of the kept squared distance;  ``knn()`` returns the index 0-based.
+    PINNED: tests/test_correspondence.py compares this restatement and the CUDA kernel bit for bit with the reference's
+    own knn.cu, compiled by oracle/build_knn_ref.py into oracle/_ref/libknn_cuda_ref.so."""
+    v, q = verts.numpy().astype(np.float32), query.numpy().astype(np.float32)
+    best = np.full(q.shape[0], np.inf, np.float32)
+    ind = np.zeros(q.shape[0], np.int64)
+    step = 256
+    for b in range(0, v.shape[0], step):
+        d = v[None, b:b + step, :] - q[:, None, :]                      # ref - query
+        ssd = (d[..., 0] * d[..., 0]).astype(np.float32)                 # fma(dx, dx, 0)
+        ssd = _fma32(d[..., 1], d[..., 1], ssd)
+        ssd = _fma32(d[..., 2], d[..., 2], ssd)
+        loc = ssd.argmin(axis=1)                                         # first minimum inside the block
+        val = ssd[np.arange(q.shape[0]), loc]
+        better = val < best                                              # strict: earlier blocks win ties
+        best = np.where(better, val, best)
+        ind = np.where(better, loc + b, ind)
+    dist = torch.from_numpy(np.sqrt(best))
+    ind = torch.from_numpy(ind)
     homo = torch.cat([query, torch.ones(query.shape[0], 1)], dim=-1)
     cano = (trans[ind] @ homo.unsqueeze(-1))[:, :3, 0]
     return dist, ind, cano, dist < thickness

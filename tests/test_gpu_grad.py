@@ -292,3 +292,52 @@ def test_fused_gradient_accumulation_matches_autograd(dev):
             assert rel_fro(got, r) <= 1e-4
     finally:
         backward_mlp.ACCUMULATE_INTO_GRAD = False
+
+
+@pytest.mark.parametrize("sigma_only", [True, False])
+def test_nerf_gradient_wrt_embedded_inputs(dev, sigma_only):
+    """The reference's own call convention with inputs that carry grad: NoF output -> Embedding -> zero-padded rows ->
+    NeRF.forward(inputs[, sigma_only=True]) (trainer/trainer_moco_flow.py:146-158,349-361).  d loss / d inputs for
+    the encoded-xyz columns (and, in full mode, the extra-feature columns) against autograd of the oracle."""
+    import moco_flow_b200 as mf
+    gen = torch.Generator().manual_seed(29)
+    N = 300
+    xyz = (torch.rand(N, 3, generator=gen) - 0.5) * 1.6
+    ncol = 63 if sigma_only else 68
+    up = torch.randn(N, 1 if sigma_only else 4, generator=gen)
+    p = orc.make_nerf_params(orc.C2F_NERF, 13, dense=True)
+    m = mf.NeRF(8, 256, 63, [4], "ind", 5)
+    m.load_state_dict(p)
+    m = m.to(dev)
+    pe = mf.Embedding(3, 10)
+    extra = torch.rand(N, 5, generator=gen) * 2 - 1
+
+    # device: xyz (leaf) -> Embedding (autograd through mcf_pe_fwd/bwd) -> padded rows -> module
+    xd = xyz.to(dev).requires_grad_(True)
+    rows = torch.zeros(N, ncol, device=dev)
+    emb = pe(xd)
+    rows[:, :emb.shape[1]] = emb
+    if not sigma_only:
+        ed = extra.to(dev).requires_grad_(True)
+        rows = torch.cat([rows[:, :63], ed], dim=1)
+    rows.retain_grad()
+    out = m(rows, sigma_only=sigma_only)
+    (out * up.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    from moco_flow_b200 import _lib as L
+    assert L.device_error_flag() == 0
+
+    po = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    xo = xyz.clone().requires_grad_(True)
+    eo = extra.clone().requires_grad_(True)
+
+    def run():
+        feats = orc.positional_encoding(xo, orc.PESpec(3, 10))
+        feats = torch.cat([feats, eo if not sigma_only else torch.zeros(N, 5)], 1)
+        o = orc.nerf_mlp(po, orc.C2F_NERF, feats, sigma_only=sigma_only)
+        return (o * up).sum()
+    leaves = [xo] + ([eo] if not sigma_only else [])
+    g32, gem = oracle_grads(run, leaves)
+    got = [("d_xyz (through Embedding)", xd.grad)] + ([("d_extra", ed.grad)] if not sigma_only else [])
+    names = [n for n, _ in got]
+    compare_grads(f"nerf-embedded-inputs[sigma_only={sigma_only}]", got, list(zip(names, gem)), 3e-2, list(zip(names, g32)))

@@ -142,7 +142,8 @@ def test_plans_carry_their_program_family():
     assert all(int(e) < 16 for e in nf.rounds["epi"]) and all(int(e) >= 16 for e in nb.rounds["epi"])
     assert int(of.rounds["epi"][-1]) == L.EPI_NOF_HEAD
     names = [f[0] for f in L.ChainParams._fields_]
-    assert names[-5:] == ["cta_pair", "program_kind", "pe_table", "wpack_bytes", "resident"]
+    assert names[-8:] == ["cta_pair", "program_kind", "pe_table", "wpack_bytes", "resident", "d_dense", "d_dense_stride",
+                          "reserved0"]
 
 
 def test_bench_reference_arm_contract():
