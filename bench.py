@@ -177,9 +177,15 @@ def self_check(workload, dev, nerfs, nofs, nerf_embs, nof_embs, n_rays: int = 25
     kw = render_kwargs(workload)
     if workload == "cfg1":
         nofs = nof_embs = o_nofs = None
+    from moco_flow_b200 import ops as _ops
+    saved_dp, _ops.RESIDUAL_DP = _ops.RESIDUAL_DP, None   # a rank-local check: no collectives (only rank 0 runs it)
+    try:
+        with torch.no_grad():
+            res = mf.render_rays(rays.to(dev), bg.to(dev), nerf_embs, nerfs, nof_embeddings=nof_embs, nof_models=nofs,
+                                 draws=draws, fused_residual_mean=True, **kw)
+    finally:
+        _ops.RESIDUAL_DP = saved_dp
     with torch.no_grad():
-        res = mf.render_rays(rays.to(dev), bg.to(dev), nerf_embs, nerfs, nof_embeddings=nof_embs, nof_models=nofs,
-                             draws=draws, fused_residual_mean=True, **kw)
         res = {k: v.cpu() for k, v in res.items()}
         out = {"rays": n_rays, "against": "oracle/moco_oracle.py on the host (fp32 reference algorithm, and the same with "
                                           "bf16 tensor-core emulation)"}
@@ -419,11 +425,16 @@ def run_ours(args):
         dbg("frame pipeline timing done")
 
     # ---- per-kernel event timing for the roofline (extra steps, not part of the numbers above) ----
+    # serial schedule here: with the weight-gradient side stream on, kernels of two streams share the GPU and a pair
+    # of events around one launch would time both
+    from moco_flow_b200 import backward_mlp
+    overlap_sms, backward_mlp.DW_OVERLAP_SMS = backward_mlp.DW_OVERLAP_SMS, 0
     L.PROFILE = []
     for _ in range(2):
         eager_step(rays_d, bg_d, tgt_d)
     torch.cuda.synchronize()
     prof, L.PROFILE = L.PROFILE, None
+    backward_mlp.DW_OVERLAP_SMS = overlap_sms
     agg = {}
     for tag, work, unit, a, b_ in prof:
         d = agg.setdefault(tag, dict(ms=0.0, work=0.0, unit=unit, n=0))
@@ -510,6 +521,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": config_dict(args.workload, world),
         "arm": {"rays_this_rank": R, "cuda_graph": graphed,
+                "dw_overlap_sms": overlap_sms if train else None,
                 "gather": (f"all_gather of [rgb, depth, opacity] = 20 B/ray inside every timed step"
                            if framed and world > 1 else None)},
         "e2e": {"value": round(total_rays / (ms_e2e * 1e-3), 1), "unit": "rays/s", "h2d_bytes_per_step": h2d,

@@ -58,7 +58,53 @@ _DW_CTAS_ENV = int(__import__('os').environ.get('MCF_DW_CTAS', '0'))
 def dw_ctas_per_job(device) -> int:
     if _DW_CTAS_ENV > 0:
         return _DW_CTAS_ENV
+    if DW_OVERLAP_SMS > 0:
+        return max(2, DW_OVERLAP_SMS // 2)
     return max(2, torch.cuda.get_device_properties(device).multi_processor_count // 2)
+
+
+# Overlap of the weight-gradient GEMMs with the backward dX chains.  The dX chain of the next MLP evaluation does not
+# depend on the weight gradients of the previous one; the GEMMs are HBM-bound (they do not need every SM to saturate
+# the memory system) and the chains are SM-bound (they leave most of the HBM bandwidth unused).  With
+# DW_OVERLAP_SMS = n > 0 (and in-place gradient accumulation, dp.FlatGradients(fused_accumulate=True)) the GEMM +
+# scatter launches go to a side stream, and every backward chain launched while one of them is in flight leaves n SMs
+# free (mcf_chain_params_t.max_ctas).  ``join_weight_gradients`` makes the current stream wait for the side stream; it
+# is called by FlatGradients before the all-reduce and by FusedAdam.step.  Works under CUDA-graph capture (fork / join
+# of the captured stream).
+DW_OVERLAP_SMS = int(__import__('os').environ.get('MCF_DW_OVERLAP_SMS', '32'))
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+_SIDE_PENDING: Dict[int, bool] = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    idx = torch.device(device).index or 0
+    st = _SIDE_STREAMS.get(idx)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[idx] = st
+    return st
+
+
+def overlap_active() -> bool:
+    return DW_OVERLAP_SMS > 0 and ACCUMULATE_INTO_GRAD
+
+
+def chain_cta_cap(device) -> int:
+    """max_ctas of a backward chain launch: leave DW_OVERLAP_SMS SMs to the weight-gradient stream while it is busy."""
+    idx = torch.device(device).index or 0
+    if not overlap_active() or not _SIDE_PENDING.get(idx):
+        return 0
+    n_sm = torch.cuda.get_device_properties(device).multi_processor_count
+    return max(2, n_sm - DW_OVERLAP_SMS) & ~1     # even: the NeRF chain runs on CTA pairs
+
+
+def join_weight_gradients() -> None:
+    """The current stream waits for every weight-gradient launch issued so far (no-op when nothing is pending)."""
+    for idx, pending in list(_SIDE_PENDING.items()):
+        if pending:
+            with torch.cuda.device(idx):
+                torch.cuda.current_stream().wait_stream(_SIDE_STREAMS[idx])
+            _SIDE_PENDING[idx] = False
 
 
 def rayfeat_images(rf: torch.Tensor, n_rows: int, rows_per_ray: int) -> torch.Tensor:
@@ -79,6 +125,25 @@ def _run_grad_plan(model, gp: P.GradPlan, st, need_dx: bool, fwd_save: torch.Ten
                    aux: Optional[torch.Tensor] = None):
     """Runs the weight-gradient GEMMs; returns the flat gradient buffer, or None when the gradients were
     accumulated in place."""
+    dev = fwd_save.device
+    if overlap_active():
+        side, main = _side_stream(dev), torch.cuda.current_stream()
+        side.wait_stream(main)
+        for t in (fwd_save, bwd_save, d_head, aux):
+            if t is not None:
+                t.record_stream(side)
+        with torch.cuda.stream(side):
+            out = _run_grad_plan_here(model, gp, st, need_dx, fwd_save, fwd_tile_bytes, bwd_save, bwd_tile_bytes, n_tiles,
+                                      d_head, wanted, aux)
+        _SIDE_PENDING[torch.device(dev).index or 0] = True
+        return out
+    return _run_grad_plan_here(model, gp, st, need_dx, fwd_save, fwd_tile_bytes, bwd_save, bwd_tile_bytes, n_tiles, d_head,
+                               wanted, aux)
+
+
+def _run_grad_plan_here(model, gp: P.GradPlan, st, need_dx: bool, fwd_save: torch.Tensor, fwd_tile_bytes: int,
+                        bwd_save: torch.Tensor, bwd_tile_bytes: int, n_tiles: int, d_head: torch.Tensor, wanted: set,
+                        aux: Optional[torch.Tensor] = None):
     dev = fwd_save.device
     staging = torch.zeros(gp.staging_floats, device=dev)
     key = (need_dx, frozenset(wanted))
@@ -197,6 +262,7 @@ class _NeRFFn(torch.autograd.Function):
         bplan = bpp.plan
         nt = _n_tiles(M)
         cp = ops.chain_params(bpp, M, ctx.S, M // ctx.S)
+        cp.max_ctas = chain_cta_cap(dev)
         cp.prologue = L.PRO_B_NERF
         g_out = g_out.contiguous()
         cp.g_out, cp.fwd_out = g_out.data_ptr(), out.data_ptr()
@@ -322,6 +388,7 @@ class _NoFFn(torch.autograd.Function):
         bplan = bpp.plan
         nt = _n_tiles(M)
         cp = ops.chain_params(bpp, M, ctx.S, M // ctx.S)
+        cp.max_ctas = chain_cta_cap(dev)
         cp.prologue = L.PRO_B_NOF
         cp.use_quat = int(model.use_quat)
         g_out = g_out.contiguous()

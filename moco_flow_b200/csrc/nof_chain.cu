@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(kNofThreads, 1) k_nof(const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 16; ++j) w16[j] = pack_bf16x2(mine[2 * j], mine[2 * j + 1]);
         tmem_st16(t_row + kColX0 + 16u * half, w16);
+        arrive();   // the tensor core only needs the TMEM operand: the HBM copy below overlaps its first layer
         if (saving && p.x0_save_off != kNofNone) {
           stage_free();
           stage32(stage, row, 32u * half, w16);
@@ -321,9 +322,9 @@ __global__ void __launch_bounds__(kNofThreads, 1) k_nof(const __grid_constant__ 
           stage32(stage, row, 32u, w16);
         }
         if (p.prologue != MCF_PRO_B_NOF && gtid == 0) atomicExch(&g_mcf_device_error, 0xBADF0000u | (uint32_t)p.prologue);
+        arrive();
         if (saving && p.x0_save_off != kNofNone) stage_store(save_tile + p.x0_save_off, kBlkN);
       }
-      arrive();
 
       // ------------------------------- rounds -------------------------------
       for (int r = 0; r < p.n_rounds; ++r) {
@@ -470,10 +471,11 @@ __global__ void __launch_bounds__(kNofThreads, 1) k_nof(const __grid_constant__ 
           if (gtid == 0) atomicExch(&g_mcf_device_error, 0xBADE0000u | (uint32_t)rd.epi);
         }
 
-        if (writes_h && saving && rd.save_off != kNofNone)
-          stage_store(save_tile + rd.save_off, ((uint32_t)rd.n_out + 63u) / 64u * kBlkN);
+        // signal the tensor core first (it needs the TMEM operand only), then push the staged image to HBM
         if (r + 1 < p.n_rounds) arrive();
         else tc_fence_before();
+        if (writes_h && saving && rd.save_off != kNofNone)
+          stage_store(save_tile + rd.save_off, ((uint32_t)rd.n_out + 63u) / 64u * kBlkN);
       }
     }
     if (gtid == 0) bulk_wait_all();

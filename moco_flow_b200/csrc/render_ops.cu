@@ -201,8 +201,8 @@ k_composite_fwd(const float* __restrict__ sigma, int sigma_stride, const float* 
   float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);  // rendering.py:164
   long long base = (long long)r * S;
   float carry = 1.0f, sw = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f;
-  // The chunks of a ray are a serial chain (the transmittance carry), so the loads of chunk c + 1 are issued before
-  // the scan of chunk c: two chunks of HBM requests in flight per warp.
+  // The chunks of a ray are a serial chain (the transmittance carry), so the loads of chunks c + 1 and c + 2 are issued
+  // before the scan of chunk c: three chunks of HBM requests in flight per warp.
   struct In { float zi, zn31, raw, c0, c1, c2, ns; };
   auto fetch = [&](int c) {
     In t = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -224,10 +224,11 @@ k_composite_fwd(const float* __restrict__ sigma, int sigma_stride, const float* 
     }
     return t;
   };
-  In nxt = fetch(0);
+  In nxt = fetch(0), nxt2 = fetch(32);   // (fetch past the end returns zeros without touching memory)
   for (int c = 0; c < S; c += 32) {
     const In cur = nxt;
-    if (c + 32 < S) nxt = fetch(c + 32);
+    nxt = nxt2;
+    if (c + 64 < S) nxt2 = fetch(c + 64);
     int i = c + lane;
     bool ok = i < S;
     float zi = cur.zi;
@@ -402,6 +403,21 @@ k_composite_bwd(const float* __restrict__ sigma, int sigma_stride, const float* 
 // -------------------------------------------------------------------------------------------------
 // sample_pdf (+ optional sort-merge with the coarse depths)
 // -------------------------------------------------------------------------------------------------
+// count of leading elements of the ascending array a[0..n) that satisfy (a[i] <= x) (kLE) or (a[i] < x): a branch-free
+// binary search with a fixed trip count (pow2 = smallest power of two >= n + 1), no divergence between the lanes
+template <bool kLE>
+__device__ __forceinline__ int count_below(const float* __restrict__ a, int n, int pow2, float x) {
+  int lo = 0;   // invariant: a[0..lo) satisfy the predicate
+#pragma unroll 1
+  for (int step = pow2 >> 1; step > 0; step >>= 1) {
+    const int probe = lo + step;
+    const float v = a[min(probe, n) - 1];
+    const bool ok = probe <= n && (kLE ? (v <= x) : (v < x));
+    lo = ok ? probe : lo;
+  }
+  return lo;
+}
+
 // One warp per ray.  Per-warp smem: cdf[nb+1] | bins[nb+1] | sorted samples [32*kEPL] | coarse z [n_coarse] |
 // merged [n_coarse + n_imp].
 // The merge with the coarse depths (rendering.py:326: sort(cat(z, samples))) does not sort 2S values: the fine samples
@@ -421,6 +437,8 @@ k_sample_pdf(const float* __restrict__ bins, int bins_stride, int bins_are_z, co
   const int r = blockIdx.x * kWarpsPerBlock + wib;
   if (r >= R) return;
   const int n_tot = n_coarse + n_imp;
+  auto pow2_above = [](int n) { int p = 1; while (p < n + 1) p <<= 1; return p; };
+  const int p2_cdf = pow2_above(nb + 1), p2_zc = pow2_above(n_coarse), p2_imp = pow2_above(n_imp);
   const int per_warp = 2 * (nb + 1) + (z_merged ? 32 * kEPL + n_coarse + n_tot : 0);
   float* s_cdf = scratch + (size_t)wib * per_warp;
   float* s_bin = s_cdf + (nb + 1);
@@ -476,11 +494,7 @@ k_sample_pdf(const float* __restrict__ bins, int bins_stride, int bins_are_z, co
     if (k < n_imp) {
       float uk = urow[k];
       // searchsorted(cdf, u, right=True): first index with cdf[idx] > u, in [0, nb+1]   (:33)
-      int lo = 0, hi = nb + 1;
-      while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (s_cdf[mid] <= uk) lo = mid + 1; else hi = mid;
-      }
+      const int lo = count_below<true>(s_cdf, nb + 1, p2_cdf, uk);
       int below = max(lo - 1, 0), above = min(lo, nb);  // :34-35
       float c0 = s_cdf[below], c1 = s_cdf[above];
       float b0 = s_bin[below], b1 = s_bin[above];
@@ -534,22 +548,12 @@ k_sample_pdf(const float* __restrict__ bins, int bins_stride, int bins_are_z, co
     const int e = q * 32 + lane;
     if (e < n_imp) {   // position = own rank + #coarse <= value
       const float x = v[q];
-      int lo = 0, hi = n_coarse;
-      while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (s_zc[mid] <= x) lo = mid + 1; else hi = mid;
-      }
-      s_out[e + lo] = x;
+      s_out[e + count_below<true>(s_zc, n_coarse, p2_zc, x)] = x;
     }
   }
   for (int j = lane; j < n_coarse; j += 32) {   // position = own rank + #samples < value
     const float x = s_zc[j];
-    int lo = 0, hi = n_imp;
-    while (lo < hi) {
-      int mid = (lo + hi) >> 1;
-      if (s_srt[mid] < x) lo = mid + 1; else hi = mid;
-    }
-    s_out[j + lo] = x;
+    s_out[j + count_below<false>(s_srt, n_imp, p2_imp, x)] = x;
   }
   __syncwarp();
   float* zo = z_merged + (long long)r * n_tot;

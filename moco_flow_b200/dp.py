@@ -101,7 +101,11 @@ class FlatGradients:
 
     def check_views(self) -> None:
         """Every ``.grad`` must still alias the flat buffer (an ``optimizer.zero_grad(set_to_none=True)`` or a
-        ``p.grad = None`` in between would silently exclude that parameter from the all-reduce)."""
+        ``p.grad = None`` in between would silently exclude that parameter from the all-reduce).  Also the point where
+        the weight-gradient side stream (backward_mlp.DW_OVERLAP_SMS) is joined: the buffer is complete after this."""
+        if self.buffer.is_cuda:
+            from . import backward_mlp
+            backward_mlp.join_weight_gradients()
         off = 0
         base = self.buffer.data_ptr()
         for p in self.params:

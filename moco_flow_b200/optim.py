@@ -135,6 +135,8 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        from . import backward_mlp
+        backward_mlp.join_weight_gradients()   # gradients accumulated on the weight-gradient side stream
         for gi, group in enumerate(self.param_groups):
             plan = self._plan(gi, group)
             if not capturing and plan["lr_host"] != float(group["lr"]):

@@ -333,7 +333,8 @@ def test_nerf_gradient_wrt_embedded_inputs(dev, sigma_only):
 
     def run():
         feats = orc.positional_encoding(xo, orc.PESpec(3, 10))
-        feats = torch.cat([feats, eo if not sigma_only else torch.zeros(N, 5)], 1)
+        if not sigma_only:
+            feats = torch.cat([feats, eo], 1)
         o = orc.nerf_mlp(po, orc.C2F_NERF, feats, sigma_only=sigma_only)
         return (o * up).sum()
     leaves = [xo] + ([eo] if not sigma_only else [])
@@ -341,3 +342,59 @@ def test_nerf_gradient_wrt_embedded_inputs(dev, sigma_only):
     got = [("d_xyz (through Embedding)", xd.grad)] + ([("d_extra", ed.grad)] if not sigma_only else [])
     names = [n for n, _ in got]
     compare_grads(f"nerf-embedded-inputs[sigma_only={sigma_only}]", got, list(zip(names, gem)), 3e-2, list(zip(names, g32)))
+
+
+def test_weight_gradient_overlap_matches_serial(dev, monkeypatch):
+    """backward_mlp.DW_OVERLAP_SMS: weight-gradient GEMMs on a side stream next to the following dX chains (which then
+    leave SMs free) -- same gradients as the serial schedule, also when replayed from a CUDA graph."""
+    import moco_flow_b200 as mf
+    from moco_flow_b200 import backward_mlp, dp
+    from moco_flow_b200.graph import CudaGraphStep
+    gen = torch.Generator().manual_seed(77)
+    R, S = 96, 64
+    rays = orc.make_rays(R, seed=5, chained=True).to(dev)
+    bg = torch.ones(R, 3, device=dev)
+    tgt = torch.rand(R, 3, generator=gen).to(dev)
+    dr = orc.make_draws(R, S, S, seed=6)
+    draws = mf.Draws(*(t.to(dev) for t in (dr.perturb, dr.noise_coarse, dr.u, dr.noise_fine)))
+    nerfs, nofs = [], []
+    for s_ in (1, 2):
+        m = mf.NeRF(8, 256, 63, [4], "ind", 5)
+        m.load_state_dict(orc.make_nerf_params(orc.C2F_NERF, s_, dense=True))
+        nerfs.append(m.to(dev))
+    for s_ in (3, 4):
+        m = mf.NoF(4, 128, 33, [2], "ind", 33, True)
+        m.load_state_dict(orc.make_nof_params(orc.C2F_NOF, s_, scale_head=0.25))
+        nofs.append(m.to(dev))
+    nerf_embs = [mf.Embedding(3, 10), mf.Embedding(1, 2), None]
+    nof_embs = [mf.Embedding(3, 5), mf.Embedding(1, 16)]
+    try:
+        flat = dp.FlatGradients(nerfs + nofs, fused_accumulate=True)
+
+        def step(rays_, bg_, tgt_):
+            flat.zero()
+            res = mf.render_rays(rays_, bg_, nerf_embs, nerfs, nof_embeddings=nof_embs, nof_models=nofs, chain_local=True,
+                                 chain_global=True, N_samples=S, N_importance=S, perturb=1.0, noise_std=0.0, draws=draws,
+                                 fused_residual_mean=True)
+            loss = mf.MSELoss()(res, tgt_) + 0.2 * sum(res[k].mean() for k in res if "disp" in k)
+            loss.backward()
+            flat.check_views()      # joins the side stream
+            return loss.detach()
+
+        step(rays, bg, tgt)
+        torch.cuda.synchronize()
+        serial = flat.buffer.clone()
+        monkeypatch.setattr(backward_mlp, "DW_OVERLAP_SMS", 48)
+        step(rays, bg, tgt)
+        torch.cuda.synchronize()
+        assert rel_fro(flat.buffer, serial) <= 1e-4
+        g = CudaGraphStep(step, [rays, bg, tgt], warmup=1)
+        flat.buffer.fill_(123.0)
+        g(rays, bg, tgt)
+        torch.cuda.synchronize()
+        from moco_flow_b200 import _lib as L
+        assert L.device_error_flag() == 0
+        assert rel_fro(flat.buffer, serial) <= 1e-4
+    finally:
+        backward_mlp.ACCUMULATE_INTO_GRAD = False
+        backward_mlp.join_weight_gradients()
