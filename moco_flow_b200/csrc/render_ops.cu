@@ -283,6 +283,122 @@ k_composite_fwd(const float* __restrict__ sigma, int sigma_stride, const float* 
   }
 }
 
+template <int kPer>
+__device__ __forceinline__ void ld_vec(const float* __restrict__ p, float* dst) {
+  if (kPer == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    dst[0] = t.x; dst[1] = t.y;
+  } else {
+#pragma unroll
+    for (int j = 0; j < kPer; j += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(p + j);
+      dst[j] = t.x; dst[j + 1] = t.y; dst[j + 2] = t.z; dst[j + 3] = t.w;
+    }
+  }
+}
+template <int kPer>
+__device__ __forceinline__ void st_vec(float* __restrict__ p, const float* src) {
+  if (kPer == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(src[0], src[1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kPer; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(src[j], src[j + 1], src[j + 2], src[j + 3]);
+  }
+}
+
+// Blocked forward for S == 32 * kPer (64 / 128 / 256 samples: every configuration of the reference's YAMLs and of
+// BASELINE.json): lane l owns the kPer CONSECUTIVE samples [l*kPer, (l+1)*kPer) of the ray, so one ray needs a single
+// warp scan (of the lanes' transmittance products) instead of one per 32 samples, all addresses are one base plus
+// immediates, there are no bounds predicates, and depths / weights / alphas move as 16-byte vectors.  ncu on the
+// chunked kernel above showed it issue-bound (85-91 % issue-active at 28-62 % of DRAM bandwidth, profiles/r02_*).
+// Same formulae; the exclusive product is associated as (product of the earlier lanes) * (product inside the lane).
+template <bool kPacked, int kPer>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_composite_fwd_blk(const float* __restrict__ sigma, const float* __restrict__ rgb, const float* __restrict__ z,
+                    const float* __restrict__ dirs, int dir_stride, const float* __restrict__ noise, float noise_std,
+                    const float* __restrict__ bg, int act, int R, float* __restrict__ weights,
+                    float* __restrict__ alphas, float* __restrict__ rgb_out, float* __restrict__ depth_out,
+                    float* __restrict__ opacity_out) {
+  constexpr int S = 32 * kPer;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const float* d = dirs + (long long)r * dir_stride;
+  const float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);  // rendering.py:164
+  const long long base = (long long)r * S + lane * kPer;
+  float zv[kPer + 1], raw[kPer], c0[kPer], c1[kPer], c2[kPer];
+  ld_vec<kPer>(z + base, zv);
+  zv[kPer] = __shfl_down_sync(kFull, zv[0], 1);   // the next lane's first depth (unused by the ray's last sample)
+  if (kPacked) {
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(rgb) + base + j);
+      c0[j] = v.x; c1[j] = v.y; c2[j] = v.z; raw[j] = v.w;
+    }
+  } else {
+    ld_vec<kPer>(sigma + base, raw);
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) c0[j] = c1[j] = c2[j] = 0.f;
+  }
+  if (noise) {
+    float ns[kPer];
+    ld_vec<kPer>(noise + base, ns);
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) raw[j] = raw[j] + ns[j] * noise_std;   // rendering.py:166,170
+  }
+  float alpha[kPer], pre[kPer];   // pre[j]: product of (1 - alpha + 1e-10) over this lane's samples before j
+  float run = 1.0f;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const bool last = (lane == 31) && (j == kPer - 1);
+    float delta = last ? 1e10f : (zv[j + 1] - zv[j]);  // rendering.py:158-160
+    delta = delta * dn;
+    alpha[j] = 1.0f - expf(-delta * density(raw[j], act));
+    pre[j] = run;
+    run = run * (1.0f - alpha[j] + 1e-10f);  // rendering.py:177
+  }
+  const float incl = warp_incl_prod(run, lane);
+  float excl = __shfl_up_sync(kFull, incl, 1);
+  if (lane == 0) excl = 1.0f;
+  float sw = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, w[kPer];
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const float T = excl * pre[j];  // exclusive cumprod, rendering.py:179
+    w[j] = alpha[j] * T;
+    sw += w[j];
+    sd += w[j] * zv[j];
+    if (kPacked) {
+      sr += w[j] * c0[j];
+      sg += w[j] * c1[j];
+      sb += w[j] * c2[j];
+    }
+  }
+  if (weights) st_vec<kPer>(weights + base, w);
+  if (alphas) st_vec<kPer>(alphas + base, alpha);
+  sw = warp_sum(sw);
+  if (kPacked) {
+    sd = warp_sum(sd);
+    sr = warp_sum(sr);
+    sg = warp_sum(sg);
+    sb = warp_sum(sb);
+  }
+  if (lane == 0) {
+    if (opacity_out) opacity_out[r] = sw;
+    if (kPacked && rgb_out) {
+      const float rem = 1.0f - sw;
+      if (bg) {  // rendering.py:189-190
+        sr = sr + bg[r * 3 + 0] * rem;
+        sg = sg + bg[r * 3 + 1] * rem;
+        sb = sb + bg[r * 3 + 2] * rem;
+      }
+      rgb_out[r * 3 + 0] = sr;
+      rgb_out[r * 3 + 1] = sg;
+      rgb_out[r * 3 + 2] = sb;
+    }
+    if (kPacked && depth_out) depth_out[r] = sd;
+  }
+}
+
 // Analytic backward (recomputes alpha/T; per-warp smem scratch holds e=exp(-delta*dens), T, delta).
 // d_sigma written at d_sigma[m*ds_stride]; d_rgb (optional) at d_rgb[m*drgb_stride+0..2].
 // kPacked: inputs and gradients are [M][4] = [r,g,b,sigma] arrays -> one 16-byte load and one 16-byte store per sample.
@@ -724,6 +840,27 @@ int mcf_composite_fwd(const float* sigma, int sigma_stride, const float* rgb, in
   // [r,g,b,sigma] rows: 16-byte vector path
   const bool packed = rgb != nullptr && sigma == rgb + 3 && sigma_stride == 4 && rgb_stride == 4 &&
                       (reinterpret_cast<uintptr_t>(rgb) & 15u) == 0;
+  // blocked kernel: S = 64 / 128 / 256, sigma either packed with rgb or a dense [R][S] array, everything 16-byte aligned
+  const bool dense_sigma = rgb == nullptr && sigma_stride == 1;
+  auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  if ((packed || dense_sigma) && (n_samples == 64 || n_samples == 128 || n_samples == 256) && al16(sigma - (packed ? 3 : 0)) &&
+      al16(z) && al16(noise) && al16(weights) && al16(alphas)) {
+#define MCF_CBLK(P_, K_)                                                                                       \
+    k_composite_fwd_blk<P_, K_><<<grid_for_warps(n_rays), kWarpsPerBlock * 32, 0, stream>>>(                   \
+        sigma, rgb, z, dirs, dir_stride, noise, noise_std, background, activation, n_rays, weights, alphas, rgb_out, \
+        depth_out, opacity_out)
+    if (packed) {
+      if (n_samples == 64) MCF_CBLK(true, 2);
+      else if (n_samples == 128) MCF_CBLK(true, 4);
+      else MCF_CBLK(true, 8);
+    } else {
+      if (n_samples == 64) MCF_CBLK(false, 2);
+      else if (n_samples == 128) MCF_CBLK(false, 4);
+      else MCF_CBLK(false, 8);
+    }
+#undef MCF_CBLK
+    return check_launch();
+  }
   if (packed)
     k_composite_fwd<true><<<grid_for_warps(n_rays), kWarpsPerBlock * 32, 0, stream>>>(
         sigma, sigma_stride, rgb, rgb_stride, z, dirs, dir_stride, noise, noise_std, background, activation, n_rays,
