@@ -486,6 +486,32 @@ def train_objective(result: Dict[str, Tensor], target: Tensor, img_w: float = 1.
 
 
 # --------------------------------------------------------------------------
+# occupancy lattice of visualize_mesh
+# --------------------------------------------------------------------------
+def density_grid(nerf: NeRFBundle, pe_xyz: PESpec, n_grid: int, frame_idx: int = -1, nof: Optional[NoFBundle] = None,
+                 nof_pes: Optional[Sequence[PESpec]] = None, num_frames: Optional[int] = None, chunk: int = 10000) -> Tensor:
+    """trainer/trainer_moco_flow.py:484-516: sigma on the N^3 lattice over [-1.5, 1.5]^3 (numpy meshgrid, 'xy'
+    indexing), optionally warped by the backward flow network of frame ``frame_idx`` (forward_nof, :160-187),
+    clamped at 0, reshaped (N, N, N)."""
+    import numpy as np
+    t = np.linspace(-1.5, 1.5, n_grid)
+    xyz = torch.FloatTensor(np.stack(np.meshgrid(t, t, t), -1).reshape(-1, 3))
+    outs = []
+    with torch.no_grad():
+        for i in range(0, xyz.shape[0], chunk):
+            x = xyz[i:i + chunk]
+            if frame_idx != -1:
+                ind = torch.tensor([frame_idx]).unsqueeze(0).repeat(x.shape[0], 1).float() * 2 / num_frames - 1.0  # :175
+                feats = torch.cat([_padded(positional_encoding(x, nof_pes[0]), nof.spec.in_channels_xyz),
+                                   _padded(positional_encoding(ind, nof_pes[1]), nof.spec.extra_feat_dim)], -1)
+                x = nof_mlp(nof.params, nof.spec, feats, x).view(-1, 3)
+            emb = _padded(positional_encoding(x, pe_xyz), nerf.spec.in_channels_xyz)
+            outs.append(nerf_mlp(nerf.params, nerf.spec, emb, sigma_only=True))
+    sigma = torch.cat(outs, 0)
+    return sigma.clamp_min(0).reshape(n_grid, n_grid, n_grid)
+
+
+# --------------------------------------------------------------------------
 # deterministic synthetic inputs shared by tests, smoke() and bench.py
 # --------------------------------------------------------------------------
 def _np_rng(seed: int):

@@ -343,3 +343,32 @@ def test_graph_replay_follows_embedding_weights(dev):
     ref = orc.nerf_mlp(orc.make_nerf_params(orc.C2F_NERF, 5, dense=True), orc.C2F_NERF, feats)
     e, _ = stats("graph replay with faded PE weights: rgb", replay[:, :3], ref[:, :3])
     assert e <= 2e-3
+
+
+@pytest.mark.parametrize("frame_idx", [-1, 37])
+def test_density_grid_matches_oracle(dev, frame_idx):
+    """The occupancy lattice of visualize_mesh (trainer/trainer_moco_flow.py:484-516), canonical and warped by the
+    backward flow network of one frame: (N, N, N) sigma volume vs the oracle."""
+    import moco_flow_b200 as mf
+    from moco_flow_b200 import aux_passes
+    N = 20
+    nerf_p = orc.make_nerf_params(orc.C2F_NERF, 61, dense=True)
+    nof_p = orc.make_nof_params(orc.C2F_NOF, 62, scale_head=0.25)
+    nerf = mf.NeRF(8, 256, 63, [4], "ind", 5)
+    nerf.load_state_dict(nerf_p)
+    nof = mf.NoF(4, 128, 33, [2], "ind", 33, True)
+    nof.load_state_dict(nof_p)
+    nerf, nof = nerf.to(dev), nof.to(dev)
+    got = aux_passes.density_grid(nerf, mf.Embedding(3, 10), N, frame_idx, nof, [mf.Embedding(3, 5), mf.Embedding(1, 16)],
+                                  num_frames=160, chunk=3000)
+    torch.cuda.synchronize()
+    _no_device_error()
+    ref = orc.density_grid(orc.NeRFBundle(orc.C2F_NERF, nerf_p), orc.C2F_PE["nerf_xyz"], N, frame_idx,
+                           orc.NoFBundle(orc.C2F_NOF, nof_p), [orc.C2F_PE["nof_xyz"], orc.C2F_PE["nof_ind"]], 160)
+    assert got.shape == (N, N, N)
+    e, sc = stats(f"density grid (frame {frame_idx})", got, ref)
+    assert e <= 1e-2 * sc
+    # the lattice itself: same points, same order as numpy's meshgrid
+    pts = aux_passes.lattice_points(5, dev).cpu()
+    t = np.linspace(-1.5, 1.5, 5)
+    assert torch.equal(pts, torch.FloatTensor(np.stack(np.meshgrid(t, t, t), -1).reshape(-1, 3)))
