@@ -238,7 +238,7 @@ typedef struct {
    * write d_dense[m*d_dense_stride + c], c < dense_cols, instead of applying the encoder's Jacobian. */
   float* d_dense;
   int32_t d_dense_stride;
-  int32_t reserved0;
+  int32_t reserved0;       /* chain.cu kernels: non-zero = signal the next layer's MMA before the training-save bulk store */
 } mcf_chain_params_t;
 
 int mcf_chain_launch(const mcf_chain_params_t* params_host, cudaStream_t stream);

@@ -825,8 +825,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
 
         tc_fence_before();
         MCF_TACC(2, te);
+        // p.reserved0 != 0: signal the tensor core BEFORE pushing the operand image to HBM (the next layer's MMA and
+        // the bulk store both only read the buffer; the barrier + bulk-copy issue then overlap the MMA)
+        const bool early = p.reserved0 != 0;
+        if (writes_h) fence_proxy_async_smem();
+        if (early && r + 1 < p.n_rounds) arrive_act_ready();
         if (writes_h) {
-          fence_proxy_async_smem();
           if (saving && rd.save_off != kNone) {
             named_bar_sync(1 + s, 128);
             if (gtid == 0) {
@@ -836,7 +840,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             store_pending = true;
           }
         }
-        if (r + 1 < p.n_rounds) arrive_act_ready();
+        if (!early && r + 1 < p.n_rounds) arrive_act_ready();
         MCF_TACC(3, te);
       }
     }

@@ -42,8 +42,29 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// Suspend-time hint of every mbarrier wait (ns; 0 = plain try_wait).  ncu (round 1 and 2) showed ~30 % of the chain
+// kernels' issued instructions in the poll loops (BRA / ISETP / SYNCS / YIELD); with the hint a waiting thread sleeps
+// inside try_wait (it is still woken as soon as the phase completes) and the loops stop competing for issue slots
+// with the MMA-issuing thread and the epilogue warps: -9 % on the 4096-ray render, -10 % on a 540x540 frame,
+// -2.4 % on the training step (profiles/r02_bench_wait_hint.json).
+#ifndef MCF_WAIT_HINT_NS
+#define MCF_WAIT_HINT_NS 20000
+#endif
+constexpr uint32_t kSpinLimit = MCF_WAIT_HINT_NS > 0 ? (1u << 22) : (1u << 26);   // bounded: flag + trap, never a hang
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if MCF_WAIT_HINT_NS > 0
+  // suspend-time hint: the thread may sleep up to this long inside one try_wait (it is still woken as soon as the
+  // phase completes), so a long wait costs a handful of poll iterations instead of thousands
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)MCF_WAIT_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -51,13 +72,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU.  ~2^28 polls is seconds; then flag + trap.
+// Bounded wait: a protocol bug must not hang the GPU.  The poll limit is seconds to a minute; then flag + trap.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > kSpinLimit) {
       atomicExch(&g_mcf_device_error, 0xDEAD0000u | tag);
       __threadfence_system();
       __trap();
@@ -168,7 +190,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > kSpinLimit) {
       atomicExch(&g_mcf_device_error, 0xDEAD0000u | tag);
       __threadfence_system();
       __trap();

@@ -357,6 +357,8 @@ def flow_residual(x_obs, x_rec, alphas, fused_mean: bool = False):
 # one-CTA-per-tile-pair path (tests/test_gpu_chain.py::test_nerf_cta_pair_matches_single), 8-9 % faster on the training
 # chains, equal on inference.  MCF_CTA_PAIR=0 selects the single-CTA path.
 CTA_PAIR = int(_os.environ.get("MCF_CTA_PAIR", "1"))
+# training chains: signal the next layer's MMA before issuing the bulk store of the saved operand image
+EARLY_ARRIVE = int(_os.environ.get("MCF_EARLY_ARRIVE", "1"))
 
 
 # bumped by writers that update parameters behind autograd's back (optim.FusedAdam writes through raw pointers, which
@@ -411,6 +413,7 @@ def chain_params(pp: PackedPlan, n_rows: int, rows_per_ray: int, n_rays: int) ->
     cp.cta_pair = CTA_PAIR if pp.plan.width == 256 else 0
     cp.program_kind = pp.plan.kind
     cp.wpack_bytes, cp.resident = pp.plan.wpack_bytes, int(pp.plan.resident)
+    cp.reserved0 = EARLY_ARRIVE
     return cp
 
 
