@@ -283,6 +283,7 @@ int mcf_dw_gemm_batch(const mcf_dw_job_t* jobs_dev, int n_jobs, const void* fwd_
 int mcf_rayfeat_image(const float* rayfeat, int rayfeat_stride, int rayfeat_dim, long long n_rows, int rows_per_ray,
                       void* out, cudaStream_t stream);
 
+#define MCF_MAX_UNPACK_PTRS 40
 /* Scatter the staging results of mcf_dw_gemm into the parameter-gradient buffer:
  * dst[dst_off + r*dst_ld + c] = transposed ? src[src_off + c*src_ld + r] : src[src_off + r*src_ld + c]. */
 typedef struct {
@@ -296,12 +297,72 @@ int mcf_unpack(const mcf_unpack_t* table_dev, int n_entries, const float* stagin
                cudaStream_t stream);
 /* Same scatter, but entry e ADDS into dst_ptrs_host[e] (+ r*dst_ld + c): accumulates straight into existing
  * parameter .grad tensors (one launch instead of one autograd add kernel per parameter). */
-#define MCF_MAX_UNPACK_PTRS 40
 int mcf_unpack_accumulate(const mcf_unpack_t* table_dev, int n_entries, const float* staging,
                           float* const* dst_ptrs_host, cudaStream_t stream);
 
 /* out[c] += sum_m src[m*stride + c], c < ncols (<= 16): bias gradients of the heads */
 int mcf_colsum(const float* src, long long n_rows, int stride, int ncols, float* out, cudaStream_t stream);
+
+/* ---- layer-program builders (host code, no CUDA calls) ---------------------------------------- */
+/* The tables above for the two network families of the path, from the module shapes alone -- what a host other
+ * than the Python shim needs to drive mcf_pack / mcf_chain_launch / mcf_dw_gemm_batch / mcf_unpack
+ * (moco_flow_b200/plans.py builds the same tables; tests/test_host_cpu.py compares the two entry by entry).
+ * Parameters are identified by canonical ids = their order in nn.Module.named_parameters():
+ *   NeRF (models/nerf.py:28-59): 2i / 2i+1 = xyz_encoding_{i+1}.0.weight / .bias (i < D), then 2D.. =
+ *        xyz_encoding_final.weight, .bias, extra_encoding.0.weight, .bias, sigma.weight, .bias, rgb.0.weight, .bias;
+ *   NoF  (models/nof.py:40-53):  2i / 2i+1 = nof_encoding_{i+1}.0.weight / .bias, 2D / 2D+1 = nof_encoding_final.*. */
+#define MCF_PLAN_MAX_PACK 192
+#define MCF_PLAN_MAX_CHUNKS 128
+#define MCF_PLAN_MAX_ROUNDS 24
+#define MCF_PLAN_MAX_LAYERS 17
+#define MCF_PLAN_MAX_JOBS 32
+typedef struct {
+  int32_t family;      /* 0: NeRF, 1: NoF                                                          */
+  int32_t D, W, cx;    /* trunk depth, hidden width (128 | 256), in_channels_xyz (<= 64)           */
+  int32_t n_skips;
+  int32_t skips[8];    /* 0-based trunk layers whose input is cat([input, h])                      */
+  int32_t extra_dim;   /* per-ray feature columns (index / direction embedding), 0: none           */
+  int32_t use_quat;    /* NoF: 9-wide quaternion head instead of the 3-wide residual head          */
+  int32_t sigma_only;  /* NeRF forward: stop after the sigma head                                  */
+  int32_t training;    /* forward: also write operand images / masks for the backward pass         */
+  int32_t need_dx;     /* backward: include the input-point gradient rounds                        */
+  int32_t nof_kernel;  /* NoF: 0 streamed weights, 1 resident (chain.cu), 2 TMEM-resident (nof_chain.cu) */
+} mcf_plan_spec_t;
+
+typedef struct {
+  int32_t n_pack, n_chunks, n_rounds, n_tensors;
+  mcf_pack_t pack[MCF_PLAN_MAX_PACK];
+  mcf_chunk_t chunks[MCF_PLAN_MAX_CHUNKS];
+  mcf_round_t rounds[MCF_PLAN_MAX_ROUNDS];
+  int32_t tensor_ids[MCF_MAX_PACK_TENSORS];   /* canonical ids in the order of the pointer array mcf_pack takes */
+  uint32_t wpack_bytes, n_consts, save_tile_bytes, mask_tile_words;
+  int32_t n_raybias, kind, resident, width;   /* kind / resident / width go into mcf_chain_params_t            */
+  /* offsets inside the per-tile save / mask records (0xFFFFFFFF: absent); h / dy are indexed by layer 1..D   */
+  uint32_t save_x0, save_feat, save_he, mask_he;
+  uint32_t save_h[MCF_PLAN_MAX_LAYERS], mask_h[MCF_PLAN_MAX_LAYERS];
+  uint32_t save_dhead, save_dye, save_dyf, save_ghead;
+  uint32_t save_dy[MCF_PLAN_MAX_LAYERS];
+} mcf_plan_t;
+
+typedef struct {
+  int32_t n_jobs, n_unpack, n_params;
+  mcf_dw_job_t jobs[MCF_PLAN_MAX_JOBS];
+  int32_t job_params[MCF_PLAN_MAX_JOBS][2];   /* canonical ids a job feeds (-1: none): clear `enabled` when neither requires grad */
+  mcf_unpack_t unpack[MCF_MAX_UNPACK_PTRS];   /* dst_off = offset in the flat layout below                     */
+  int32_t unpack_param[MCF_MAX_UNPACK_PTRS];  /* ... or parameter id + float offset inside it (mcf_unpack_accumulate) */
+  uint32_t unpack_inner[MCF_MAX_UNPACK_PTRS];
+  uint32_t staging_floats;
+  int32_t head_ncols, head_stride;            /* mcf_colsum of the fp32 head gradients -> staging + head_off   */
+  uint32_t head_off;
+  uint32_t param_offset[MCF_MAX_PACK_TENSORS];/* flat gradient layout: parameters in canonical order, 16-byte aligned */
+  uint32_t total_floats;
+} mcf_grad_plan_t;
+
+int mcf_plan_forward(const mcf_plan_spec_t* spec, mcf_plan_t* out);
+int mcf_plan_backward(const mcf_plan_spec_t* spec, const mcf_plan_t* forward_plan, mcf_plan_t* out);
+int mcf_plan_gradients(const mcf_plan_spec_t* spec, const mcf_plan_t* forward_plan, const mcf_plan_t* backward_plan,
+                       mcf_grad_plan_t* out);
+
 
 /* One Adam step over n contiguous fp32 elements (parameters, gradients and both moments are flat device arrays):
  * torch.optim.Adam(lr, betas, eps, weight_decay) as built by trainer/base.py:122-133 and stepped at

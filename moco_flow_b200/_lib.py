@@ -75,6 +75,7 @@ EXPORTS = [
     "mcf_ray_bias", "mcf_composite_fwd", "mcf_composite_bwd", "mcf_sample_pdf", "mcf_masked_l1_fwd",
     "mcf_masked_l1_finalize", "mcf_masked_l1_bwd", "mcf_pack", "mcf_chain_launch", "mcf_dw_gemm", "mcf_dw_gemm_batch", "mcf_rayfeat_image", "mcf_unpack",
     "mcf_unpack_accumulate", "mcf_colsum", "mcf_adam_step", "mcf_make_rays", "mcf_canvas_scatter", "mcf_nearest_vertex",
+    "mcf_plan_forward", "mcf_plan_backward", "mcf_plan_gradients",
 ]
 
 _lib = None
@@ -130,6 +131,12 @@ def check(code: int, what: str) -> None:
     if code != 0:
         kind = "cudaError" if code > 0 else "MCF_ERR"
         raise MocoFlowLibraryError(f"{what} failed: {kind} {code}")
+
+
+def check_rc(code: int, what: str) -> None:
+    """Return-code check of an entry that launches nothing (not counted as a GPU launch)."""
+    if code != 0:
+        raise MocoFlowLibraryError(f"{what} failed: {'cudaError' if code > 0 else 'MCF_ERR'} {code}")
 
 
 def ptr(t) -> C.c_void_p:

@@ -29,6 +29,7 @@ UNITS = [
     ("optim.cu", []),
     ("camera.cu", ["-fmad=false"]),
     ("correspondence.cu", ["-fmad=false"]),
+    ("plan_host.cu", []),
 ]
 HEADERS = [os.path.join(CSRC, "ptx.cuh"), os.path.join(CSRC, "nof_math.cuh"),
            os.path.join(ROOT, "include", "moco_flow_b200.h")]

@@ -158,3 +158,78 @@ def test_bench_reference_arm_contract():
     assert line["metric"].startswith("train rays/s") and line["value"] > 0 and line["steps"] == 1
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def _same_plan(cp, pp, names):
+    """C-built plan == plans.py plan: every table entry, size and named offset."""
+    from moco_flow_b200 import plans_c
+    assert (cp.n_pack, cp.n_chunks, cp.n_rounds) == (len(pp.pack), len(pp.chunks), len(pp.rounds))
+    assert [names[cp.tensor_ids[i]] for i in range(cp.n_tensors)] == pp.tensor_names
+    for name, dt, n, ref in (("pack", L.PACK_DT, cp.n_pack, pp.pack), ("chunks", L.CHUNK_DT, cp.n_chunks, pp.chunks),
+                             ("rounds", L.ROUND_DT, cp.n_rounds, pp.rounds)):
+        got = cp.table(name, dt, n)
+        assert got.tobytes() == np.ascontiguousarray(ref).tobytes(), name
+    assert (cp.wpack_bytes, cp.n_consts, cp.save_tile_bytes, cp.mask_tile_words) == \
+        (pp.wpack_bytes, pp.n_consts, pp.save_tile_bytes, pp.mask_tile_words)
+    assert (cp.n_raybias, cp.kind, cp.resident, cp.width) == (pp.n_raybias, pp.kind, int(pp.resident), pp.width)
+    for key, off in pp.offsets.items():
+        kind, what = key.split("_", 1)
+        if what[0] == "h" and what[1:].isdigit():
+            got = (cp.save_h if kind == "save" else cp.mask_h)[int(what[1:])]
+        elif what.startswith("dy") and what[2:].isdigit():
+            got = cp.save_dy[int(what[2:])]
+        else:
+            got = getattr(cp, key)
+        assert got == off, key
+
+
+@pytest.mark.parametrize("nof_kernel", [0, 1, 2])
+def test_c_abi_plan_builders_match_python(nof_kernel, monkeypatch):
+    """the MLP entries of the C ABI need layer-program tables.  mcf_plan_forward / _backward /
+    _gradients build them inside the library; they must equal what plans.py builds, entry by entry."""
+    from moco_flow_b200 import plans_c
+    from moco_flow_b200.build import build
+    build()
+    monkeypatch.setattr(P, "NOF_RESIDENT", nof_kernel != 0)
+    monkeypatch.setattr(P, "NOF_KERNEL", "ts" if nof_kernel == 2 else "smem")
+    cases = [(0, 8, 256, 63, (4,), 5, False), (0, 8, 256, 63, (4,), 27, False), (0, 8, 256, 63, (4,), 0, False),
+             (1, 4, 128, 33, (2,), 33, True), (1, 4, 128, 33, (2,), 33, False), (1, 6, 128, 33, (2, 4), 33, True)]
+    for family, D, W, cx, skips, extra, quat in cases:
+        names = plans_c.parameter_names(family, D)
+        for training in (False, True):
+            for sigma_only in ((False, True) if family == 0 else (False,)):
+                s = plans_c.spec(family, D, W, cx, skips, extra, quat, sigma_only, training, nof_kernel=nof_kernel)
+                cf = plans_c.forward(s)
+                pf = P.nerf_forward_plan(D, W, cx, skips, extra, sigma_only, training) if family == 0 else \
+                    P.nof_forward_plan(D, W, cx, skips, extra, quat, training)
+                _same_plan(cf, pf, names)
+        for need_dx in (False, True):
+            s = plans_c.spec(family, D, W, cx, skips, extra, quat, False, True, need_dx, nof_kernel)
+            cf = plans_c.forward(s)
+            cb = plans_c.backward(s, cf)
+            if family == 0:
+                pf = P.nerf_forward_plan(D, W, cx, skips, extra, False, True)
+                pb = P.nerf_backward_plan(D, W, cx, skips, extra, need_dx, pf)
+                mod = mf.NeRF(D, W, cx, list(skips), "ind" if extra else "none", extra)
+            else:
+                pf = P.nof_forward_plan(D, W, cx, skips, extra, quat, True)
+                pb = P.nof_backward_plan(D, W, cx, skips, extra, quat, need_dx, pf)
+                mod = mf.NoF(D, W, cx, list(skips), "ind", extra, quat)
+            _same_plan(cb, pb, names)
+            shapes = {k: tuple(v.shape) for k, v in mod.named_parameters()}
+            assert list(shapes) == names
+            pg = P.nerf_grad_plan(D, W, cx, skips, extra, shapes, pf, pb) if family == 0 else \
+                P.nof_grad_plan(D, W, cx, skips, extra, quat, shapes, pf, pb)
+            cg = plans_c.gradients(s, cf, cb)
+            assert cg.n_jobs == len(pg.jobs) and cg.n_unpack == len(pg.unpack) and cg.n_params == len(names)
+            jobs = np.frombuffer(bytes(cg.jobs), dtype=L.DWJOB_DT)[:cg.n_jobs]
+            assert jobs.tobytes() == P.job_table(pg, set(names)).tobytes()
+            unp = np.frombuffer(bytes(cg.unpack), dtype=L.UNPACK_DT)[:cg.n_unpack]
+            assert unp.tobytes() == np.ascontiguousarray(pg.unpack).tobytes()
+            assert [(names[cg.unpack_param[i]], cg.unpack_inner[i]) for i in range(cg.n_unpack)] == pg.unpack_targets
+            assert (cg.staging_floats, cg.total_floats) == (pg.staging_floats, pg.total_floats)
+            assert (cg.head_ncols, cg.head_stride, cg.head_off) == tuple(pg.head_colsum)
+            assert [cg.param_offset[i] for i in range(len(names))] == [pg.param_offsets[n] for n in names]
+            for ji, j in enumerate(pg.jobs):
+                fed = {names[k] for k in cg.job_params[ji] if k >= 0}
+                assert fed == set(j.params), (ji, fed, j.params)
