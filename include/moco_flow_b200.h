@@ -7,7 +7,7 @@
  *
  * The reference (wyysf-98/MoCo_Flow) has no FFI: its boundary for this path is a set of Python
  * callables.  Each entry below names the reference code it replaces (paths relative to the
- * reference root); `moco_flow_b200/*.py` re-creates the Python callables on top of these entries
+ * reference root); the Python modules of `moco_flow_b200/` re-creates the Python callables on top of these entries
  * and INTEGRATION.md shows the import switch a maintainer makes.
  */
 #ifndef MOCO_FLOW_B200_H_

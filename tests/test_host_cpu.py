@@ -233,3 +233,10 @@ def test_c_abi_plan_builders_match_python(nof_kernel, monkeypatch):
             for ji, j in enumerate(pg.jobs):
                 fed = {names[k] for k in cg.job_params[ji] if k >= 0}
                 assert fed == set(j.params), (ji, fed, j.params)
+
+
+def test_c_example_compiles(tmp_path):
+    """examples/nerf_forward.c drives a NeRF forward through the C ABI alone (plan builder -> pack -> ray bias -> chain
+    launch); it must compile against include/moco_flow_b200.h with a plain C compiler."""
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-c", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "nerf_forward.c"), "-o", str(tmp_path / "ex.o")])
