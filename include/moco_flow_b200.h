@@ -127,7 +127,9 @@ typedef struct {
   uint8_t a_buf;    /* 0: input block X0, 1: activation buffer H */
   uint8_t a_kblock; /* 64-column block of that buffer            */
   uint8_t ksteps;   /* K=16 MMAs issued from this chunk (1..4)   */
-  uint8_t flags;    /* bit0: first MMA overwrites the accumulator */
+  uint8_t flags;    /* bit0: first MMA overwrites the accumulator; bit1: this chunk and the next are the 128-row halves
+                     * of one [256 x 64] weight tile; bit3: one CTA's halves of this tile and of the next k-block's
+                     * tile are adjacent in the packed stream (CTA pairs: one 32 KB copy)                       */
   uint16_t n;       /* MMA N                                       */
   uint16_t acc_col; /* accumulator column offset inside the slot   */
 } mcf_chunk_t;
@@ -327,6 +329,8 @@ typedef struct {
   int32_t training;    /* forward: also write operand images / masks for the backward pass         */
   int32_t need_dx;     /* backward: include the input-point gradient rounds                        */
   int32_t nof_kernel;  /* NoF: 0 streamed weights, 1 resident (chain.cu), 2 TMEM-resident (nof_chain.cu) */
+  int32_t no_pair_merge; /* width 256: 0 = lay each layer's weight tiles out half by half, so that the CTA-pair kernel
+                          * fetches one CTA's share of two k-blocks with one 32 KB copy (chunk flag bit 3); 1 = k-block major */
 } mcf_plan_spec_t;
 
 typedef struct {

@@ -301,11 +301,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             if (C == 1 && tile_of(pair, s) >= n_tiles) continue;
             for (int c = cb; c < ce; ++c) {
               uint32_t bytes = tab.chunks[c].bytes, src_off = tab.chunks[c].src_off;
+              bool merge = false;
               if (C == 2) {
-                if (tab.chunks[c].flags & 2u) {   // [256 x 64] weight tile: this CTA's 128-row half is one chunk
+                const uint32_t fl = tab.chunks[c].flags;
+                if (fl & 2u) {   // [256 x 64] weight tile: this CTA's 128-row half is one chunk
                   bytes = tab.chunks[c + cta_rank].bytes;
                   src_off = tab.chunks[c + cta_rank].src_off;
                   ++c;
+                  // flag bit 3: this CTA's halves of this k-block and of the next one are adjacent in the packed
+                  // stream -> ONE 32 KB copy into two consecutive ring stages (not across the ring's wrap).  A bulk-copy issue costs the
+                  // thread ~330 clk whatever its size: 16 KB copies sustain 24 B/clk, a pair tile needs 32 B/clk.
+                  merge = (fl & 8u) != 0u && stage != (uint32_t)(kStages - 1);
+                  if (merge) { bytes += kBlk; c += 2; }
                 } else {                          // single chunk: this CTA's half of its rows
                   bytes >>= 1;
                   src_off += cta_rank * bytes;
@@ -314,12 +321,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
               if (turn == me) {
                 MCF_T0(tw);
                 wait_x(&tab.w_empty[stage], phase ^ 1u, 0x100u | stage);
+                if (merge) wait_x(&tab.w_empty[stage + 1], phase ^ 1u, 0x100u | (stage + 1));
                 MCF_TACC(0, tw);
                 mbar_arrive_expect_tx(&tab.w_full[stage], bytes);
                 bulk_g2s(smem + L::off_ring + stage * kBlk, wsrc + src_off, bytes, &tab.w_full[stage]);
               }
               if (++turn == kProducers) turn = 0;
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              if (merge) { if (++stage == kStages) { stage = 0; phase ^= 1u; } }
             }
           }
         }
@@ -330,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     // =========================== MMA issuer ===========================
     if (lane == 0 && C == 2 && cta_rank != 0u) {
       // ---- peer CTA of a pair: relay "my half of the stage has landed" to the leader's MMA thread ----
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, fph = 0;   // fph: per-stage phase bits of w_full (a merged copy skips the odd stage's barrier)
       uint32_t peer_bar[kStages];
       for (int i = 0; i < kStages; ++i) peer_bar[i] = map_to_cta(smem_u32(&tab.w_peer[i]), 0u);
       for (long long pair = unit0; pair < n_pairs; pair += unit_step) {
@@ -338,16 +347,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
           const int cb = tab.rounds[r].chunk_begin, ce = tab.rounds[r].chunk_end;
           for (int s = 0; s < 2; ++s) {
             for (int c = cb; c < ce; ++c) {
-              if (tab.chunks[c].flags & 2u) ++c;
-              mbar_wait(&tab.w_full[stage], phase, 0x500u | stage);
+              const uint32_t fl = tab.chunks[c].flags;
+              bool merge = false;
+              if (fl & 2u) {
+                ++c;
+                merge = (fl & 8u) != 0u && stage != (uint32_t)(kStages - 1);
+                if (merge) c += 2;
+              }
+              mbar_wait(&tab.w_full[stage], (fph >> stage) & 1u, 0x500u | stage);
+              fph ^= 1u << stage;
               mbar_arrive_cluster_relaxed(peer_bar[stage]);
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              stage = (stage + (merge ? 2u : 1u)) & (kStages - 1);
             }
           }
         }
       }
     } else if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, fph = 0, pph = 0;   // per-stage phase bits of w_full / w_peer
       uint32_t ar_phase[2] = {0u, 0u};
       const uint32_t h_addr = smem_u32(smem + L::off_h), x0_addr = smem_u32(smem + L::off_x0);
       const uint32_t ring_addr = smem_u32(smem + L::off_ring);
@@ -366,13 +382,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             tc_fence_after();
             MCF_TACC(0, tm);
             for (int c = cb; c < ce; ++c) {
-              if (!kRes) mbar_wait(&tab.w_full[stage], phase, 0x300u | stage);
+              if (!kRes) {
+                mbar_wait(&tab.w_full[stage], (fph >> stage) & 1u, 0x300u | stage);
+                fph ^= 1u << stage;
+              }
               const mcf_chunk_t ch = tab.chunks[c];
               // flag bit1: this chunk and the next one are the two 128-row halves of one [256 x 64] weight tile
               // sitting in consecutive (even, odd) ring stages -> one N=256 instruction per K step
               const bool fuse = (ch.flags & 2u) != 0u;   // resident variant: the two images are adjacent in the stream
-              if (C == 2) mbar_wait(&tab.w_peer[stage], phase, 0x600u | stage);
-              else if (fuse && !kRes) mbar_wait(&tab.w_full[stage + 1], phase, 0x300u | (stage + 1));
+              // CTA pairs: one 32 KB copy per CTA may carry this k-block and the next one (see the producer)
+              const bool merge = C == 2 && fuse && (ch.flags & 8u) != 0u && stage != (uint32_t)(kStages - 1);
+              if (C == 2) {
+                mbar_wait(&tab.w_peer[stage], (pph >> stage) & 1u, 0x600u | stage);
+                pph ^= 1u << stage;
+              } else if (fuse && !kRes) {
+                mbar_wait(&tab.w_full[stage + 1], (fph >> (stage + 1)) & 1u, 0x300u | (stage + 1));
+                fph ^= 1u << (stage + 1);
+              }
               if (!kRes) tc_fence_after();
               MCF_TACC(1, tm);
               // resident variant: x0 is block 0 of the slot's activation buffer, weights sit at their stream offset
@@ -401,14 +427,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
                 if (fuse) ++c;   // nothing to release
               } else if (C == 2) {
                 umma_commit_pair(&tab.w_empty[stage], 3);   // frees the stage in both CTAs
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                stage = (stage + 1u) & (kStages - 1);
                 if (fuse) ++c;
+                if (merge) {   // the next k-block of the same layer sits in the following (odd) stage
+                  const mcf_chunk_t c2 = tab.chunks[c + 1];
+                  const uint32_t a2 = ((c2.a_buf) ? (h_addr + s * L::kHBytes) : (x0_addr + s * kBlk)) + c2.a_kblock * kBlk;
+                  const uint64_t ad2 = make_sdesc(a2, 0u, 1024u), bd2 = make_sdesc(ring_addr + stage * kBlk, 0u, 1024u);
+                  const uint32_t d2 = tmem_base + s * kSlotCols + c2.acc_col;
+#pragma unroll
+                  for (uint32_t k = 0; k < 4; ++k)
+                    umma_bf16_pair(d2, ad2 + 2u * k, bd2 + 2u * k, idesc, (k || !(c2.flags & 1u)) ? 1u : 0u);
+                  umma_commit_pair(&tab.w_empty[stage], 3);
+                  stage = (stage + 1u) & (kStages - 1);
+                  c += 2;
+                }
               } else {
                 umma_commit(&tab.w_empty[stage]);
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                stage = (stage + 1u) & (kStages - 1);
                 if (fuse) {
                   umma_commit(&tab.w_empty[stage]);
-                  if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                  stage = (stage + 1u) & (kStages - 1);
                   ++c;
                 }
               }

@@ -23,8 +23,9 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 struct Builder {
   mcf_plan_t* p;
   int err = 0;
+  bool pair_layout = false;   // width 256: tiles of a layer laid out half by half (see mcf_plan_spec_t.no_pair_merge)
 
-  explicit Builder(mcf_plan_t* out, int width) : p(out) {
+  explicit Builder(mcf_plan_t* out, int width, bool pair = false) : p(out), pair_layout(pair && width == 256) {
     memset(p, 0, sizeof(*p));
     p->width = width;
     const uint32_t none = kNone;
@@ -73,13 +74,35 @@ struct Builder {
       mcf_chunk_t& b = p->chunks[p->n_chunks - 1];
       if (a.a_buf == b.a_buf && a.a_kblock == b.a_kblock && a.ksteps == b.ksteps && (a.flags & 1) == (b.flags & 1) &&
           a.n == b.n && a.n == 128 && a.bytes == kBlk && b.bytes == kBlk && b.acc_col == a.acc_col + 128 &&
-          b.src_off == a.src_off + kBlk)
+          (b.src_off == a.src_off + kBlk || pair_layout))
         a.flags |= 2;
     }
+  }
+  // the [NH*128 x 64] weight tiles of k-blocks 0..nkb-1 of one layer: images in stream order, chunks in consumption
+  // order (k-block major, then the 128-row halves)
+  template <typename F>
+  void tiles(F image_of, int nkb, int NH, int a_buf, int acc0, int init_kb) {
+    Img imgs[8][2];
+    if (pair_layout && NH == 2) {
+      for (int nh = 0; nh < NH; ++nh)
+        for (int kb = 0; kb < nkb; ++kb) imgs[kb][nh] = image_of(kb, nh);
+    } else {
+      for (int kb = 0; kb < nkb; ++kb)
+        for (int nh = 0; nh < NH; ++nh) imgs[kb][nh] = image_of(kb, nh);
+    }
+    for (int kb = 0; kb < nkb; ++kb)
+      for (int nh = 0; nh < NH; ++nh) chunk(imgs[kb][nh], a_buf, kb, 4, 128, acc0 + nh * 128, kb == init_kb);
   }
   void round(int epi, int n_out, int acc_col, int chunk_begin, int raybias = -1, uint32_t const_off = 0,
              uint32_t aux_off = 0, uint32_t save_off = kNone, uint32_t mask_off = kNone) {
     if (p->n_rounds >= MCF_PLAN_MAX_ROUNDS) { err = MCF_ERR_UNSUPPORTED; return; }
+    // flag bit 3: one CTA's halves of this pair tile and of the next k-block's are adjacent in the stream
+    for (int c = chunk_begin; c + 3 < p->n_chunks; ++c) {
+      mcf_chunk_t &a = p->chunks[c], &a1 = p->chunks[c + 1], &b = p->chunks[c + 2], &b1 = p->chunks[c + 3];
+      if ((a.flags & 2) && (b.flags & 2) && (c - chunk_begin) % 2 == 0 && a.a_buf == b.a_buf && b.a_kblock == a.a_kblock + 1 &&
+          a.ksteps == 4 && b.ksteps == 4 && !(b.flags & 1) && b.src_off == a.src_off + kBlk && b1.src_off == a1.src_off + kBlk)
+        a.flags |= 8;
+    }
     mcf_round_t& r = p->rounds[p->n_rounds++];
     r.epi = (uint16_t)epi; r.n_out = (uint16_t)n_out; r.acc_col = (uint16_t)acc_col;
     r.chunk_begin = (uint16_t)chunk_begin; r.chunk_end = (uint16_t)p->n_chunks; r.raybias = (int16_t)raybias;
@@ -143,23 +166,20 @@ bool nof_resident_ok(const mcf_plan_spec_t& s) {
 }
 
 int nerf_forward(const mcf_plan_spec_t& s, mcf_plan_t* out) {
-  Builder b(out, s.W);
+  Builder b(out, s.W, !s.no_pair_merge);
   const int W = s.W, D = s.D, cx = s.cx, nkb = W / 64, NH = W / 128, kx = ceil_div(cx, 16);
   if (s.training) b.save_slot(&out->save_x0, 1);
   for (int i = 0; i < D; ++i) {
     const bool skip = is_skip(s, i);
     const int ld = i == 0 ? cx : (skip ? W + cx : W);
     const int c0 = out->n_chunks;
-    int si = 0;
-    if (i == 0 || skip) {
-      for (int nh = 0; nh < NH; ++nh) b.chunk(b.image(id_trunk_w(i), nh * 128, 128, 0, cx, ld, false, 128), 0, 0, kx, 128, nh * 128, si == 0);
-      ++si;
-    }
+    const bool has_x0 = i == 0 || skip;
+    if (has_x0)
+      for (int nh = 0; nh < NH; ++nh) b.chunk(b.image(id_trunk_w(i), nh * 128, 128, 0, cx, ld, false, 128), 0, 0, kx, 128, nh * 128, true);
     if (i > 0) {
       const int base = skip ? cx : 0;
-      for (int kb = 0; kb < nkb; ++kb, ++si)
-        for (int nh = 0; nh < NH; ++nh)
-          b.chunk(b.image(id_trunk_w(i), nh * 128, 128, base + 64 * kb, 64, ld, false, 128), 1, kb, 4, 128, nh * 128, si == 0);
+      b.tiles([&](int kb, int nh) { return b.image(id_trunk_w(i), nh * 128, 128, base + 64 * kb, 64, ld, false, 128); }, nkb, NH, 1,
+              0, has_x0 ? -1 : 0);
     }
     const uint32_t boff = b.konst(id_trunk_b(i), 0, 1, 0, W, W);
     const bool last = i == D - 1;
@@ -174,9 +194,7 @@ int nerf_forward(const mcf_plan_spec_t& s, mcf_plan_t* out) {
   }
   if (!s.sigma_only) {
     int c0 = out->n_chunks;
-    for (int kb = 0; kb < nkb; ++kb)
-      for (int nh = 0; nh < NH; ++nh)
-        b.chunk(b.image(id_final_w(s), nh * 128, 128, 64 * kb, 64, W, false, 128), 1, kb, 4, 128, nh * 128, kb == 0);
+    b.tiles([&](int kb, int nh) { return b.image(id_final_w(s), nh * 128, 128, 64 * kb, 64, W, false, 128); }, nkb, NH, 1, 0, 0);
     uint32_t boff = b.konst(id_final_b(s), 0, 1, 0, W, W);
     b.round(MCF_EPI_LINEAR, W, 0, c0, -1, boff, 0, s.training ? b.save_slot(&out->save_feat, nkb) : kNone);
     const int half = W / 2;
@@ -252,29 +270,24 @@ void bwd_trunk(Builder& b, const mcf_plan_spec_t& s, const mcf_plan_t& fwd, int 
     if (i == 0) break;
     const int base = skip ? cin_extra : 0;
     const int c0 = out->n_chunks;
-    for (int kb = 0; kb < nkb; ++kb)
-      for (int nh = 0; nh < NH; ++nh)
-        b.chunk(b.image(id_trunk_w(i), base + nh * 128, 128, 64 * kb, 64, ld, true, 128), 1, kb, 4, 128, nh * 128, kb == 0);
+    b.tiles([&](int kb, int nh) { return b.image(id_trunk_w(i), base + nh * 128, 128, 64 * kb, 64, ld, true, 128); }, nkb, NH, 1, 0, 0);
     b.round(MCF_EPI_B_MASK, W, 0, c0, -1, 0, 0, b.save_slot(&out->save_dy[i], nkb), fwd.mask_h[i]);
   }
 }
 
 int nerf_backward(const mcf_plan_spec_t& s, const mcf_plan_t& fwd, mcf_plan_t* out) {
   if (s.W != 256) return MCF_ERR_UNSUPPORTED;
-  Builder b(out, s.W);
+  Builder b(out, s.W, !s.no_pair_merge);
   const int W = s.W, D = s.D, nkb = W / 64, NH = W / 128, half = W / 2;
   b.save_slot(&out->save_dhead, 1);
   b.save_slot(&out->save_dye, ceil_div(half, 64));
   int c0 = out->n_chunks;
-  for (int kb = 0; kb < ceil_div(half, 64); ++kb)
-    for (int nh = 0; nh < NH; ++nh)
-      b.chunk(b.image(id_extra_w(s), nh * 128, 128, 64 * kb, 64, W + s.extra_dim, true, 128), 1, kb, 4, 128, nh * 128, kb == 0);
+  b.tiles([&](int kb, int nh) { return b.image(id_extra_w(s), nh * 128, 128, 64 * kb, 64, W + s.extra_dim, true, 128); },
+          ceil_div(half, 64), NH, 1, 0, 0);
   const uint32_t wrgb = b.konst(id_rgb_w(s), 0, 3, 0, half, half);
   b.round(MCF_EPI_B_LINEAR, W, 0, c0, -1, 0, wrgb, b.save_slot(&out->save_dyf, nkb), fwd.mask_he);
   c0 = out->n_chunks;
-  for (int kb = 0; kb < nkb; ++kb)
-    for (int nh = 0; nh < NH; ++nh)
-      b.chunk(b.image(id_final_w(s), nh * 128, 128, 64 * kb, 64, W, true, 128), 1, kb, 4, 128, nh * 128, kb == 0);
+  b.tiles([&](int kb, int nh) { return b.image(id_final_w(s), nh * 128, 128, 64 * kb, 64, W, true, 128); }, nkb, NH, 1, 0, 0);
   const uint32_t wsig = b.konst(id_sigma_w(s), 0, 1, 0, W, W);
   b.round(MCF_EPI_B_MASK_SIGMA, W, 0, c0, -1, 0, wsig, b.save_slot(&out->save_dy[D], nkb), fwd.mask_h[D]);
   bwd_trunk(b, s, fwd, 0);

@@ -28,6 +28,11 @@ NOF_RESIDENT = os.environ.get("MCF_NOF_RESIDENT", "1") != "0"
 # which resident kernel: "ts" = nof_chain.cu (activations in tensor memory, mcf_chain_params_t.resident = 2),
 # "smem" = chain.cu's resident variant (resident = 1)
 NOF_KERNEL = os.environ.get("MCF_NOF_KERNEL", "ts")
+# Width-256 programs: lay the weight tiles of a layer out half by half ([kb0 nh0][kb1 nh0]..[kb0 nh1][kb1 nh1]..), so
+# that ONE CTA's share of consecutive k-blocks is contiguous in the packed stream; the CTA-pair kernel then fetches two
+# k-blocks with one 32 KB bulk copy instead of two 16 KB ones (a copy issue costs its thread ~330 clk whatever the size:
+# 24 B/clk with 16 KB copies, while a pair tile consumes 32 B/clk per CTA at the MMA's peak rate).
+PAIR_MERGE = os.environ.get("MCF_PAIR_MERGE", "1") != "0"
 RES_BYTES = 147456
 
 
@@ -55,6 +60,7 @@ class Plan:
 class _Builder:
     def __init__(self, width: int):
         self.width = width
+        self.pair_layout = PAIR_MERGE and width == 256
         self.names: List[str] = []
         self.pack: List[tuple] = []
         self.chunks: List[tuple] = []
@@ -94,14 +100,41 @@ class _Builder:
         # Two consecutive 128-row halves of the same [256 x 64] weight tile landing in an (even, odd) pair of ring
         # stages are one contiguous 32 KB K-major tile: mark the first so the kernel issues N=256 instructions
         # (halves the A-operand shared-memory reads per FLOP).
+        # (In the ring kernels the two halves become adjacent in shared memory whatever their stream offsets; the
+        # resident-weight kernel reads the stream itself and needs them adjacent there.)
         if FUSE_N256 and len(self.chunks) >= 2 and len(self.chunks) % 2 == 0:
             a, b = self.chunks[-2], self.chunks[-1]
             if (a[2], a[3], a[4], a[5] & 1, a[6]) == (b[2], b[3], b[4], b[5] & 1, b[6]) and a[6] == 128 \
-                    and a[1] == BLK and b[1] == BLK and b[7] == a[7] + 128 and b[0] == a[0] + BLK:
+                    and a[1] == BLK and b[1] == BLK and b[7] == a[7] + 128 \
+                    and (b[0] == a[0] + BLK or self.pair_layout):
                 a[5] |= 2
+
+    def tiles(self, img_args, kbs: Sequence[int], NH: int, a_buf: int, acc0: int, init_kb: int) -> None:
+        """The [NH*128 x 64] weight tiles of the k-blocks ``kbs`` of one layer: images in stream order, chunks in
+        consumption order (kb major, then the 128-row halves).  ``img_args(kb, nh)`` -> arguments of ``image``."""
+        imgs = {}
+        if self.pair_layout and NH == 2:
+            for nh in range(NH):
+                for kb in kbs:
+                    imgs[(kb, nh)] = self.image(*img_args(kb, nh))
+        else:
+            for kb in kbs:
+                for nh in range(NH):
+                    imgs[(kb, nh)] = self.image(*img_args(kb, nh))
+        for kb in kbs:
+            for nh in range(NH):
+                self.chunk(imgs[(kb, nh)], a_buf, kb, 4, 128, acc0 + nh * 128, init=(kb == init_kb))
 
     def round(self, epi: int, n_out: int, acc_col: int, chunk_begin: int, raybias: int = -1, const_off: int = 0,
               aux_off: int = 0, save_off: int = L.NONE, mask_off: int = L.NONE) -> None:
+        # flag bit 3 on the first chunk of a pair tile: this CTA's halves of this k-block and of the next one are
+        # adjacent in the stream (pair layout) -> the CTA-pair kernel may fetch both with one 32 KB copy
+        ch = self.chunks
+        for c in range(chunk_begin, len(ch) - 3):
+            a, a1, b, b1 = ch[c], ch[c + 1], ch[c + 2], ch[c + 3]
+            if (a[5] & 2) and (b[5] & 2) and (c - chunk_begin) % 2 == 0 and a[2] == b[2] and b[3] == a[3] + 1 \
+                    and a[4] == 4 and b[4] == 4 and not (b[5] & 1) and b[0] == a[0] + BLK and b1[0] == a1[0] + BLK:
+                a[5] |= 8
         self.rounds.append((epi, n_out, acc_col, chunk_begin, len(self.chunks), raybias, const_off, aux_off,
                             save_off, mask_off, 0))
 
@@ -161,10 +194,15 @@ def nerf_forward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: 
         wname, bname = f"xyz_encoding_{i+1}.0.weight", f"xyz_encoding_{i+1}.0.bias"
         ld = cx if i == 0 else (W + cx if i in skips else W)
         c0 = len(b.chunks)
-        for si, (abuf, kb, ks, col0, ncols) in enumerate(_trunk_sources(i, skips, cx, nkb, 0)):
+        kx = _ceil(cx, 16)
+        has_x0 = i == 0 or i in skips
+        if has_x0:
             for nh in range(NH):
-                img = b.image(wname, nh * 128, 128, col0, ncols, ld, False, 128)
-                b.chunk(img, abuf, kb, ks, 128, nh * 128, init=(si == 0))
+                b.chunk(b.image(wname, nh * 128, 128, 0, cx, ld, False, 128), 0, 0, kx, 128, nh * 128, init=True)
+        if i > 0:
+            base = cx if i in skips else 0
+            b.tiles(lambda kb, nh: (wname, nh * 128, 128, base + 64 * kb, 64, ld, False, 128), list(range(nkb)), NH, 1, 0,
+                    -1 if has_x0 else 0)
         boff = b.const(bname, 0, 1, 0, W, W)
         last = i == D - 1
         aux = 0
@@ -177,10 +215,8 @@ def nerf_forward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim: 
                 mask_off=mask)
     if not sigma_only:
         c0 = len(b.chunks)
-        for kb in range(nkb):
-            for nh in range(NH):
-                img = b.image("xyz_encoding_final.weight", nh * 128, 128, 64 * kb, 64, W, False, 128)
-                b.chunk(img, 1, kb, 4, 128, nh * 128, init=(kb == 0))
+        b.tiles(lambda kb, nh: ("xyz_encoding_final.weight", nh * 128, 128, 64 * kb, 64, W, False, 128), list(range(nkb)),
+                NH, 1, 0, 0)
         boff = b.const("xyz_encoding_final.bias", 0, 1, 0, W, W)
         b.round(L.EPI_LINEAR, W, 0, c0, const_off=boff, save_off=b.save_slot("feat", nkb) if training else L.NONE)
         half = W // 2
@@ -368,10 +404,7 @@ def _bwd_trunk(b: _Builder, fwd: Plan, D: int, W: int, cx: int, skips, skip_extr
             break
         base = cin_extra if is_skip else 0
         c0 = len(b.chunks)
-        for kb in range(nkb):
-            for nh in range(NH):
-                img = b.image(wname, base + nh * 128, 128, 64 * kb, 64, ld, True, 128)
-                b.chunk(img, 1, kb, 4, 128, nh * 128, init=(kb == 0))
+        b.tiles(lambda kb, nh: (wname, base + nh * 128, 128, 64 * kb, 64, ld, True, 128), list(range(nkb)), NH, 1, 0, 0)
         b.round(L.EPI_B_MASK, W, 0, c0, save_off=b.save_slot(f"dy{i}", nkb), mask_off=fwd.offsets[f"mask_h{i}"])
 
 
@@ -398,19 +431,15 @@ def nerf_backward_plan(D: int, W: int, cx: int, skips: Sequence[int], extra_dim:
     b.save_slot("dye", _ceil(half, 64))
     # round 0: through extra_encoding (feat part)
     c0 = len(b.chunks)
-    for kb in range(_ceil(half, 64)):
-        for nh in range(NH):
-            img = b.image("extra_encoding.0.weight", nh * 128, 128, 64 * kb, 64, W + extra_dim, True, 128)
-            b.chunk(img, 1, kb, 4, 128, nh * 128, init=(kb == 0))
+    b.tiles(lambda kb, nh: ("extra_encoding.0.weight", nh * 128, 128, 64 * kb, 64, W + extra_dim, True, 128),
+            list(range(_ceil(half, 64))), NH, 1, 0, 0)
     wrgb = b.const("rgb.0.weight", 0, 3, 0, half, half)
     b.round(L.EPI_B_LINEAR, W, 0, c0, aux_off=wrgb, save_off=b.save_slot("dyf", nkb),
             mask_off=fwd.offsets["mask_he"])
     # round 1: through xyz_encoding_final, add the sigma head, mask with h_D
     c0 = len(b.chunks)
-    for kb in range(nkb):
-        for nh in range(NH):
-            img = b.image("xyz_encoding_final.weight", nh * 128, 128, 64 * kb, 64, W, True, 128)
-            b.chunk(img, 1, kb, 4, 128, nh * 128, init=(kb == 0))
+    b.tiles(lambda kb, nh: ("xyz_encoding_final.weight", nh * 128, 128, 64 * kb, 64, W, True, 128), list(range(nkb)), NH,
+            1, 0, 0)
     wsig = b.const("sigma.weight", 0, 1, 0, W, W)
     b.round(L.EPI_B_MASK_SIGMA, W, 0, c0, aux_off=wsig, save_off=b.save_slot(f"dy{D}", nkb),
             mask_off=fwd.offsets[f"mask_h{D}"])

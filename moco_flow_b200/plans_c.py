@@ -19,7 +19,7 @@ _i32, _u32 = C.c_int32, C.c_uint32
 class PlanSpec(C.Structure):
     _fields_ = [("family", _i32), ("D", _i32), ("W", _i32), ("cx", _i32), ("n_skips", _i32), ("skips", _i32 * 8),
                 ("extra_dim", _i32), ("use_quat", _i32), ("sigma_only", _i32), ("training", _i32), ("need_dx", _i32),
-                ("nof_kernel", _i32)]
+                ("nof_kernel", _i32), ("no_pair_merge", _i32)]
 
 
 class CPlan(C.Structure):
@@ -50,7 +50,8 @@ class CGradPlan(C.Structure):
 
 
 def spec(family: int, D: int, W: int, cx: int, skips: Sequence[int], extra_dim: int, use_quat: bool = False,
-         sigma_only: bool = False, training: bool = False, need_dx: bool = False, nof_kernel: int = 2) -> PlanSpec:
+         sigma_only: bool = False, training: bool = False, need_dx: bool = False, nof_kernel: int = 2,
+         pair_merge: bool = True) -> PlanSpec:
     s = PlanSpec()
     s.family, s.D, s.W, s.cx, s.extra_dim = family, D, W, cx, extra_dim
     s.n_skips = len(skips)
@@ -58,6 +59,7 @@ def spec(family: int, D: int, W: int, cx: int, skips: Sequence[int], extra_dim: 
         s.skips[i] = k
     s.use_quat, s.sigma_only, s.training, s.need_dx, s.nof_kernel = int(use_quat), int(sigma_only), int(training), \
         int(need_dx), nof_kernel
+    s.no_pair_merge = int(not pair_merge)
     return s
 
 
