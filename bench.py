@@ -151,11 +151,30 @@ class Clocks:
         return out
 
 
-def build_models(dev, seed: int = 0):
+def synthetic_weights():
+    """Random-init weights of the c2f.yaml shapes (configs/.../c2f.yaml:44-102) for both arms, from a numpy stream so
+    every rank and both arms hold the same values.  nn.Linear's default init leaves the fine-pass density head
+    non-positive over the whole volume (every opacity exactly 0, the image = the background), which would make the
+    self-check of the fine outputs vacuous; the density heads are therefore re-centred the way the parity tests do
+    (oracle.make_nerf_params(dense=True)): same shapes, same arithmetic, semi-transparent rays."""
+    from oracle import moco_oracle as orc
+    nerf_p = [orc.make_nerf_params(orc.C2F_NERF, s, dense=True) for s in (1, 2)]
+    nof_p = [orc.make_nof_params(orc.C2F_NOF, s, scale_head=0.25) for s in (3, 4)]
+    return nerf_p, nof_p
+
+
+def build_models(dev):
     import moco_flow_b200 as mf
-    torch.manual_seed(seed)  # random-init weights of the c2f.yaml shapes (configs/.../c2f.yaml:44-102)
-    nerfs = [mf.NeRF(8, 256, 63, [4], "ind", 5).to(dev) for _ in range(2)]
-    nofs = [mf.NoF(4, 128, 33, [2], "ind", 33, True).to(dev) for _ in range(2)]
+    nerf_p, nof_p = synthetic_weights()
+    nerfs, nofs = [], []
+    for p in nerf_p:
+        m = mf.NeRF(8, 256, 63, [4], "ind", 5)
+        m.load_state_dict(p)
+        nerfs.append(m.to(dev))
+    for p in nof_p:
+        m = mf.NoF(4, 128, 33, [2], "ind", 33, True)
+        m.load_state_dict(p)
+        nofs.append(m.to(dev))
     nerf_embs = [mf.Embedding(3, 10), mf.Embedding(1, 2), None]
     nof_embs = [mf.Embedding(3, 5), mf.Embedding(1, 16)]
     return nerfs, nofs, nerf_embs, nof_embs
@@ -556,8 +575,7 @@ def cpu_step_fn(workload: str, n_rays: int, device: str = "cpu"):
     from oracle import moco_oracle as orc
     torch.manual_seed(0)
     pes = orc.C2F_PE
-    nerf_p = [orc.make_nerf_params(orc.C2F_NERF, s) for s in (1, 2)]
-    nof_p = [orc.make_nof_params(orc.C2F_NOF, s) for s in (3, 4)]
+    nerf_p, nof_p = synthetic_weights()
     train = workload == "train"
     for p in nerf_p + nof_p:
         for k in p:

@@ -786,10 +786,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
             uint32_t v[32];
             float f[32];
             tmem_ld32(t_acc + c0, v);
-            uint32_t word = 0xFFFFFFFFu;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j == (c0 >> 5)) word = mwords[j];
+            // select tree over registers (an indexed read would put the eight words in local memory)
+            const int ci = c0 >> 5;
+            const uint32_t s01 = (ci & 1) ? mwords[1] : mwords[0], s23 = (ci & 1) ? mwords[3] : mwords[2];
+            const uint32_t s45 = (ci & 1) ? mwords[5] : mwords[4], s67 = (ci & 1) ? mwords[7] : mwords[6];
+            const uint32_t s03 = (ci & 2) ? s23 : s01, s47 = (ci & 2) ? s67 : s45;
+            const uint32_t word = (ci & 4) ? s47 : s03;
             tmem_ld_wait();
             if (!kNoF && rd.epi == MCF_EPI_B_MASK_SIGMA) {
               float ws[32];
