@@ -39,6 +39,12 @@ constexpr int kMaxChunks = 128;
 constexpr int kMaxRounds = 24;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr uint32_t kSlotCols = 256;
+// training saves: 1 = every epilogue warp stores its own rows of the operand image, 0 = one store per image by the
+// epilogue group's first thread behind a group barrier
+#ifndef MCF_CHAIN_WARP_STORE
+#define MCF_CHAIN_WARP_STORE 1
+#endif
+constexpr bool kWarpStore = MCF_CHAIN_WARP_STORE != 0;
 
 struct Tables {
   mcf_chunk_t chunks[kMaxChunks];  // 2048 B
@@ -488,6 +494,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
     };
     uint32_t af_phase = 0;
     bool store_pending = false;
+    // Training saves.  A thread owns a tile row, so a warp's 32 rows of every 64-column block are 4 KB contiguous in
+    // the swizzled image: with kWarpStore each warp pushes its own pieces to HBM (lane 0 issues and later waits for
+    // them) and the epilogue group needs no barrier around the stores; otherwise the group's first thread stores
+    // the whole image after a group barrier.
+    auto store_image = [&](uint8_t* dst, const uint8_t* src, uint32_t n_blocks) {
+      if (kWarpStore) {
+        __syncwarp();   // every lane has executed fence.proxy.async after its st.shared
+        if (lane == 0) {
+          for (uint32_t b = 0; b < n_blocks; ++b) {
+            const uint32_t off = b * kBlk + (uint32_t)qtr * 4096u;
+            bulk_s2g(dst + off, src + off, 4096u);
+          }
+          bulk_commit();
+        }
+      } else {
+        named_bar_sync(1 + s, 128);
+        if (gtid == 0) {
+          bulk_s2g(dst, src, n_blocks * kBlk);
+          bulk_commit();
+        }
+      }
+      store_pending = true;
+    };
+    auto store_read_done = [&]() {   // an earlier store no longer reads the buffers about to be overwritten
+      if (store_pending) {
+        if (kWarpStore) {
+          if (lane == 0) bulk_wait_read_all();
+          __syncwarp();
+        } else {
+          if (gtid == 0) bulk_wait_read_all();
+          named_bar_sync(1 + s, 128);
+        }
+        store_pending = false;
+      }
+    };
 
     for (long long pair = unit0; pair < n_pairs; pair += unit_step) {
       const long long tile = tile_of(pair, s);
@@ -506,11 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
 
       MCF_T0(te);
       // make sure an earlier bulk store no longer reads the buffers we are about to overwrite
-      if (store_pending) {
-        if (gtid == 0) bulk_wait_read_all();
-        named_bar_sync(1 + s, 128);
-        store_pending = false;
-      }
+      store_read_done();
 
       // ------------------------- prologue: build the first operand -------------------------
       if (!kBwd && p.prologue == MCF_PRO_PE_XYZ) {
@@ -638,14 +675,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
       fence_proxy_async_smem();
       if (saving && p.x0_save_off != kNone) {
         // the prologue's operand is itself needed by the weight-gradient GEMM: store its image
-        named_bar_sync(1 + s, 128);
-        if (gtid == 0) {
-          const bool fwd = !kBwd;
-          const uint32_t nbytes = fwd ? kBlk : (p.prologue == MCF_PRO_B_NERF ? (uint32_t)(W / 2 / 64) * kBlk : kBlk);
-          bulk_s2g(save_tile + p.x0_save_off, fwd ? x0buf : hbuf, nbytes);
-          bulk_commit();
-        }
-        store_pending = true;
+        const bool fwd = !kBwd;
+        const uint32_t n_blocks = fwd ? 1u : (p.prologue == MCF_PRO_B_NERF ? (uint32_t)(W / 2 / 64) : 1u);
+        store_image(save_tile + p.x0_save_off, fwd ? x0buf : hbuf, n_blocks);
       }
       arrive_act_ready();
       MCF_TACC(0, te);
@@ -675,11 +707,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         MCF_TACC(1, te);
         const bool writes_h = rd.epi != MCF_EPI_NOF_HEAD && rd.epi != MCF_EPI_B_DPE &&
                               !(rd.epi == MCF_EPI_NERF_RGB && !saving);
-        if (writes_h && store_pending) {
-          if (gtid == 0) bulk_wait_read_all();
-          named_bar_sync(1 + s, 128);
-          store_pending = false;
-        }
+        if (writes_h) store_read_done();
         const uint32_t t_acc = t_row + rd.acc_col;
 
         if (!kBwd && (rd.epi == MCF_EPI_RELU || rd.epi == MCF_EPI_RELU_SIGMA || rd.epi == MCF_EPI_LINEAR)) {
@@ -871,20 +899,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain(const __grid_constant__ m
         if (writes_h) fence_proxy_async_smem();
         if (early && r + 1 < p.n_rounds) arrive_act_ready();
         if (writes_h) {
-          if (saving && rd.save_off != kNone) {
-            named_bar_sync(1 + s, 128);
-            if (gtid == 0) {
-              bulk_s2g(save_tile + rd.save_off, hbuf, ((uint32_t)rd.n_out + 63u) / 64u * kBlk);
-              bulk_commit();
-            }
-            store_pending = true;
-          }
+          if (saving && rd.save_off != kNone) store_image(save_tile + rd.save_off, hbuf, ((uint32_t)rd.n_out + 63u) / 64u);
         }
         if (!early && r + 1 < p.n_rounds) arrive_act_ready();
         MCF_TACC(3, te);
       }
     }
-    if (gtid == 0) bulk_wait_all();
+    if (kWarpStore ? lane == 0 : gtid == 0) bulk_wait_all();
     if (timing && gtid == 0) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) p.timing[blockIdx.x * 16 + s * 4 + j] = tacc[j];

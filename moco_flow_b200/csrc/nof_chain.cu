@@ -59,6 +59,16 @@ struct NofSmem {
 };
 static_assert(NofSmem<true>::total <= 232448, "shared memory budget exceeded");
 
+// How the training saves (operand images for the weight-gradient GEMM) reach HBM:
+//   0 = staged in shared memory, one bulk store of the whole image by the epilogue group's first thread (group barriers)
+//   1 = staged, every epilogue warp bulk-stores its own 32 rows of the full-width rounds (no group barrier per round)
+//   2 = no staging: every thread writes its row's 16-byte pieces straight to the image in HBM (no barrier, no wait)
+#ifndef MCF_NOF_WARP_STORE
+#define MCF_NOF_WARP_STORE 1
+#endif
+constexpr bool kWarpStore = MCF_NOF_WARP_STORE == 1;
+constexpr bool kDirectSave = MCF_NOF_WARP_STORE == 2;
+
 __device__ __forceinline__ void ld32f(const float* __restrict__ p, float (&b)[32]) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -70,7 +80,7 @@ __device__ __forceinline__ void ld32f(const float* __restrict__ p, float (&b)[32
   }
 }
 
-// 16 packed bf16x2 words (32 columns starting at col0) -> the 128B-swizzled staging image
+// 16 packed bf16x2 words (32 columns starting at col0) -> the 128B-swizzled operand image (staging copy or HBM record)
 __device__ __forceinline__ void stage32(uint8_t* img, uint32_t row, uint32_t col0, const uint32_t (&w)[16]) {
   const uint32_t block = col0 >> 6, c16 = (col0 & 63u) >> 3;
 #pragma unroll
@@ -185,13 +195,37 @@ __global__ void __launch_bounds__(kNofThreads, 1) k_nof(const __grid_constant__ 
     uint8_t* stage = smem + L::off_stage + (kSave ? s * 2u * kBlkN : 0u);
     const uint32_t t_row = tmem_base + ((uint32_t)(qtr * 32) << 16) + s * kSlotStride;
     uint32_t af_phase = 0;
-    bool store_pending = false;
-    auto stage_free = [&]() {      // an earlier bulk store must have finished reading the staging image
+    bool store_pending = false;   // a store of the whole staging image issued by the group's first thread
+    bool warp_pending = false;    // stores of this warp's own 32 rows issued by its lane 0
+    auto stage_free = [&]() {      // earlier bulk stores must have finished reading what is about to be overwritten
+      if (kSave && kWarpStore && warp_pending) {
+        if (lane == 0) bulk_wait_read_all();
+        __syncwarp();
+        warp_pending = false;
+      }
       if (kSave && store_pending) {
         if (gtid == 0) bulk_wait_read_all();
         named_bar_sync(1 + s, kEpiThreads);
         store_pending = false;
       }
+    };
+    // A warp's 32 rows of one 64-column block are 4 KB contiguous in the swizzled image (a row is 128 B): in the
+    // full-width rounds each warp owns such a piece outright and pushes it to HBM itself -- no group-wide barrier.
+    auto warp_store = [&](uint8_t* dst, uint32_t block) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t off = block * kBlkN + (uint32_t)qtr * 4096u;
+        bulk_s2g(dst + off, stage + off, 4096u);
+        bulk_commit();
+      }
+      warp_pending = true;
+    };
+    // the x0 image is written by both column halves of a row (two warps): once the warps run unsynchronised through
+    // the rounds, the first write of a tile has to wait for the other half's last store as well
+    auto stage_free_shared = [&]() {
+      stage_free();
+      if (kSave && kWarpStore) named_bar_sync(1 + s, kEpiThreads);
     };
     auto stage_store = [&](uint8_t* dst, uint32_t nbytes) {   // staging image -> save record
       fence_proxy_async_smem();
@@ -271,9 +305,13 @@ __global__ void __launch_bounds__(kNofThreads, 1) k_nof(const __grid_constant__ 
         tmem_st16(t_row + kColX0 + 16u * half, w16);
         arrive();   // the tensor core only needs the TMEM operand: the HBM copy below overlaps its first layer
         if (saving && p.x0_save_off != kNofNone) {
-          stage_free();
-          stage32(stage, row, 32u * half, w16);
-          stage_store(save_tile + p.x0_save_off, kBlkN);
+          if (kDirectSave) {
+            stage32(save_tile + p.x0_save_off, row, 32u * half, w16);
+          } else {
+            stage_free_shared();
+            stage32(stage, row, 32u * half, w16);
+            stage_store(save_tile + p.x0_save_off, kBlkN);
+          }
         }
       } else {
         // backward of the flow head (models/nof.py:75-82): d{v,s,t} as a K = 16 operand, dL/dx into dx
@@ -308,22 +346,22 @@ __global__ void __launch_bounds__(kNofThreads, 1) k_nof(const __grid_constant__ 
           for (int j = 0; j < 8; ++j) w8[j] = pack_bf16x2(d16[2 * j], d16[2 * j + 1]);
           tmem_st8(t_row + kColH, w8);
           if (saving && p.x0_save_off != kNofNone) {
-            stage_free();
+            if (!kDirectSave) stage_free_shared();
             uint32_t w16[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) w16[j] = j < 8 ? w8[j] : 0u;
-            stage32(stage, row, 0u, w16);
+            stage32(kDirectSave ? save_tile + p.x0_save_off : stage, row, 0u, w16);
           }
         } else if (saving && p.x0_save_off != kNofNone) {
-          stage_free();
+          if (!kDirectSave) stage_free_shared();
           uint32_t w16[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) w16[j] = 0u;
-          stage32(stage, row, 32u, w16);
+          stage32(kDirectSave ? save_tile + p.x0_save_off : stage, row, 32u, w16);
         }
         if (p.prologue != MCF_PRO_B_NOF && gtid == 0) atomicExch(&g_mcf_device_error, 0xBADF0000u | (uint32_t)p.prologue);
         arrive();
-        if (saving && p.x0_save_off != kNofNone) stage_store(save_tile + p.x0_save_off, kBlkN);
+        if (!kDirectSave && saving && p.x0_save_off != kNofNone) stage_store(save_tile + p.x0_save_off, kBlkN);
       }
 
       // ------------------------------- rounds -------------------------------
@@ -347,7 +385,7 @@ __global__ void __launch_bounds__(kNofThreads, 1) k_nof(const __grid_constant__ 
         af_phase ^= 1u;
         tc_fence_after();
         const uint32_t t_acc = t_row + rd.acc_col;
-        if (writes_h && saving && rd.save_off != kNofNone) stage_free();
+        if (!kDirectSave && writes_h && saving && rd.save_off != kNofNone) stage_free();
 
         if (relu_round) {
           const bool want_mask = kSave && p.masks != nullptr && rd.mask_off != kNofNone;
@@ -376,7 +414,8 @@ __global__ void __launch_bounds__(kNofThreads, 1) k_nof(const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 16; ++j) w16[j] = cvt_bf16x2_relu_bits(v[2 * j], v[2 * j + 1]);
             tmem_st16(t_row + kColH + (uint32_t)(c0 >> 1), w16);
-            if (saving && rd.save_off != kNofNone) stage32(stage, row, (uint32_t)c0, w16);
+            if (saving && rd.save_off != kNofNone)
+              stage32(kDirectSave ? save_tile + rd.save_off : stage, row, (uint32_t)c0, w16);
           }
         } else if (!kBwd && rd.epi == MCF_EPI_NOF_HEAD) {
           if (half == 0) {
@@ -418,7 +457,8 @@ __global__ void __launch_bounds__(kNofThreads, 1) k_nof(const __grid_constant__ 
               w16[j] = cvt_bf16x2_bits(lo, hi);
             }
             tmem_st16(t_row + kColH + (uint32_t)(c0 >> 1), w16);
-            if (saving && rd.save_off != kNofNone) stage32(stage, row, (uint32_t)c0, w16);
+            if (saving && rd.save_off != kNofNone)
+              stage32(kDirectSave ? save_tile + rd.save_off : stage, row, (uint32_t)c0, w16);
           }
         } else if (kBwd && rd.epi == MCF_EPI_B_DPE) {
           // d_xyz += J_PE(x)^T dPE, with sin/cos taken from the saved first-layer operand image (half 0 owns dx)
@@ -474,11 +514,13 @@ __global__ void __launch_bounds__(kNofThreads, 1) k_nof(const __grid_constant__ 
         // signal the tensor core first (it needs the TMEM operand only), then push the staged image to HBM
         if (r + 1 < p.n_rounds) arrive();
         else tc_fence_before();
-        if (writes_h && saving && rd.save_off != kNofNone)
-          stage_store(save_tile + rd.save_off, ((uint32_t)rd.n_out + 63u) / 64u * kBlkN);
+        if (!kDirectSave && writes_h && saving && rd.save_off != kNofNone) {
+          if (kWarpStore && rd.n_out == 128) warp_store(save_tile + rd.save_off, (uint32_t)half);
+          else stage_store(save_tile + rd.save_off, ((uint32_t)rd.n_out + 63u) / 64u * kBlkN);
+        }
       }
     }
-    if (gtid == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
   }
 
   // ---- teardown ----
