@@ -88,10 +88,6 @@ def main():
         p = os.path.join(OUT, f"prof_{tag}_{src}_raw.csv")
         if os.path.exists(p):
             full(p, tag, rnd)
-    for name in ("bench_train.json", "bench_render.json"):
-        p = os.path.join(OUT, name)
-        if os.path.exists(p) and os.path.getsize(p) > 0:
-            open(os.path.join(DST, f"{rnd}_{name}"), "w").write(open(p).read())
 
 
 if __name__ == "__main__":

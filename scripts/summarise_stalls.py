@@ -1,6 +1,6 @@
 """Aggregate the `ncu --page source --csv` exports of the chain kernels into profiles/<round>_stalls_chain.json.
 
-usage: python scripts/summarise_stalls.py <capture-suffix> <round>     e.g.  r02f r02
+usage: python scripts/summarise_stalls.py <capture-suffix[,older-suffix...]> <round>     e.g.  r02g,r02f r02
 
 Reads gpurun_out/prof_chain_{render,train}_<suffix>_source.csv (written by scripts/gpu_profile_r02.sh).  ncu prints
 every launch twice; the repeated block is dropped.  Per kernel: share of warp-stall samples per reason, and the instruction mix as the share of
@@ -86,9 +86,12 @@ def main():
                    "and instruction mix (share of executed warp instructions); BRA/ISETP/SYNCS are mostly the "
                    "bounded mbarrier poll loops"}
     for leg in ("render", "train"):
-        p = os.path.join(ROOT, "gpurun_out", "prof_chain_%s_%s_source.csv" % (leg, suffix))
-        if os.path.exists(p):
-            doc[leg] = summarise(p)
+        for sfx in suffix.split(","):     # several captures: the first one that has this leg
+            p = os.path.join(ROOT, "gpurun_out", "prof_chain_%s_%s_source.csv" % (leg, sfx))
+            if os.path.exists(p):
+                doc[leg] = summarise(p)
+                doc[leg + "_capture"] = sfx
+                break
     dst = os.path.join(ROOT, "profiles", "%s_stalls_chain.json" % rnd)
     with open(dst, "w") as f:
         json.dump(doc, f, indent=1)
