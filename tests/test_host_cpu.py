@@ -160,6 +160,28 @@ def test_bench_reference_arm_contract():
     assert line["e2e"] == {"value": line["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_bench_weights_make_the_self_check_meaningful():
+    """bench.py checks its timed computation against the oracle; with nn.Linear's default init the fine-pass density is
+    non-positive everywhere (all opacities exactly 0, image = background) and that check would compare constants.  The
+    bench's synthetic weights must give semi-transparent-to-opaque rays on the bench's own synthetic rays."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from oracle import moco_oracle as orc
+    import torch
+    rays, bg, _ = bench.synth_batch(32, seed=1)
+    nerf_p, nof_p = bench.synthetic_weights()
+    pes = orc.C2F_PE
+    with torch.no_grad():
+        res = orc.render_rays(rays, bg, [pes["nerf_xyz"], pes["nerf_ind"], None],
+                              [orc.NeRFBundle(orc.C2F_NERF, p) for p in nerf_p], [pes["nof_xyz"], pes["nof_ind"]],
+                              [orc.NoFBundle(orc.C2F_NOF, p) for p in nof_p], **bench.render_kwargs("render"))
+    assert float(res["opacity_fine"].min()) > 0.5
+    assert float((res["rgb_fine"] - bg).abs().max()) > 0.05      # not the background
+    assert float(res["depth_fine"].std()) > 0.0
+
+
 def _same_plan(cp, pp, names):
     """C-built plan == plans.py plan: every table entry, size and named offset."""
     from moco_flow_b200 import plans_c
