@@ -152,8 +152,9 @@ class _Builder:
 
     def finish(self, n_raybias: int = 0, kind: int = 0, resident: int = 0) -> Plan:
         self.chunks = [tuple(c) for c in self.chunks]
-        assert len(self.chunks) <= 128 and len(self.rounds) <= 24 and len(self.names) <= 32, \
-            (len(self.chunks), len(self.rounds), len(self.names))
+        if len(self.chunks) > 128 or len(self.rounds) > 24 or len(self.names) > 32:
+            raise ValueError(f"network too deep for one fused launch: {len(self.chunks)} weight chunks (max 128), "
+                             f"{len(self.rounds)} layer rounds (max 24), {len(self.names)} parameter tensors (max 32)")
         assert not resident or self.wbytes <= RES_BYTES
         return Plan(self.width, list(self.names),
                     np.array(self.pack, dtype=L.PACK_DT), np.array(self.chunks, dtype=L.CHUNK_DT),

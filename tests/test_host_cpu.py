@@ -215,7 +215,9 @@ def test_c_abi_plan_builders_match_python(nof_kernel, monkeypatch):
     monkeypatch.setattr(P, "NOF_RESIDENT", nof_kernel != 0)
     monkeypatch.setattr(P, "NOF_KERNEL", "ts" if nof_kernel == 2 else "smem")
     cases = [(0, 8, 256, 63, (4,), 5, False), (0, 8, 256, 63, (4,), 27, False), (0, 8, 256, 63, (4,), 0, False),
-             (1, 4, 128, 33, (2,), 33, True), (1, 4, 128, 33, (2,), 33, False), (1, 6, 128, 33, (2, 4), 33, True)]
+             (1, 4, 128, 33, (2,), 33, True), (1, 4, 128, 33, (2,), 33, False), (1, 6, 128, 33, (2, 4), 33, True),
+             (0, 4, 256, 39, (), 0, False), (0, 8, 256, 63, (2, 5), 5, False), (0, 8, 256, 27, (4,), 5, False),
+             (1, 3, 128, 33, (), 33, True), (1, 4, 128, 21, (1,), 8, False)]
     for family, D, W, cx, skips, extra, quat in cases:
         names = plans_c.parameter_names(family, D)
         for training in (False, True):
@@ -255,6 +257,18 @@ def test_c_abi_plan_builders_match_python(nof_kernel, monkeypatch):
             for ji, j in enumerate(pg.jobs):
                 fed = {names[k] for k in cg.job_params[ji] if k >= 0}
                 assert fed == set(j.params), (ji, fed, j.params)
+
+
+def test_plan_builders_refuse_the_same_shapes():
+    """Shapes outside what the fused kernels support: plans.py raises ValueError, the C builders return MCF_ERR_*."""
+    from moco_flow_b200 import plans_c
+    from moco_flow_b200.build import build
+    build()
+    for family, D, W, cx, skips, extra in ((0, 8, 192, 63, (4,), 5), (0, 8, 256, 70, (4,), 5), (0, 30, 256, 63, (4,), 5)):
+        with pytest.raises(ValueError):
+            P.nerf_forward_plan(D, W, cx, skips, extra, False, False)
+        with pytest.raises(L.MocoFlowLibraryError):
+            plans_c.forward(plans_c.spec(family, D, W, cx, skips, extra, False, False, False))
 
 
 def test_c_example_compiles(tmp_path):
