@@ -1,6 +1,7 @@
 """CPU restatement of the reference's ray generation / canvas scatter.  TEST INFRASTRUCTURE ONLY (see oracle/__init__):
-imported by tests/, never by the product path.  Pinned against fixtures produced by the reference's own
-utils/camera.py (tests/golden/make_golden.py -> tests/golden/camera.npz)."""
+imported by tests/, never by the product path.  Pinned against fixtures produced by the reference's own code:
+utils/camera.py (tests/golden/make_golden_camera.py -> tests/golden/camera.npz) and MoCoFlowTrainer.render
+(tests/golden/make_golden_canvas.py -> tests/golden/canvas.npz)."""
 import numpy as np
 import torch
 

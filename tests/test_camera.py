@@ -26,6 +26,23 @@ def test_camera_oracle_matches_reference_fixture(golden, name):
     assert np.array_equal(d_cam.numpy(), g[f"{name}_rays_d_cam"])
 
 
+@pytest.fixture(scope="module")
+def canvas_golden(golden_dir):
+    return dict(np.load(os.path.join(golden_dir, "canvas.npz")))
+
+
+@pytest.mark.parametrize("name", ["fine", "coarse"])
+def test_canvas_oracle_matches_reference_fixture(canvas_golden, name):
+    """The image / depth assembly of the reference's own MoCoFlowTrainer.render (trainer/trainer_moco_flow.py:249-263,
+    run by tests/golden/make_golden_canvas.py) against the oracle restatement: bit for bit."""
+    g = canvas_golden
+    img, dep = cam_orc.canvas_scatter(torch.from_numpy(g[f"{name}_background"]), g[f"{name}_rays_msk"],
+                                      torch.from_numpy(g[f"{name}_rgb"]), torch.from_numpy(g[f"{name}_depth"]),
+                                      torch.from_numpy(g[f"{name}_opacity"]))
+    assert np.array_equal(img.numpy(), g[f"{name}_img"]) and np.array_equal(dep.numpy(), g[f"{name}_depth_img"])
+    assert (g[f"{name}_opacity"] == 0).any() and (g[f"{name}_depth_img"] == 8).any() and (g[f"{name}_depth_img"] == 10).any()
+
+
 def test_canvas_oracle_semantics():
     P = 10
     bg = torch.arange(P * 3, dtype=torch.float32).view(P, 3)
@@ -71,6 +88,20 @@ def test_make_rays_kernel(golden, name):
     cam_frame = camera.make_rays(H, W, cam.focal[0], cam.center, None, near, far, idx, device=dev).cpu().numpy()
     assert np.abs(cam_frame[:, 3:6] - g[f"{name}_rays_d_cam"]).max() <= 2.5e-7 and not cam_frame[:, :3].any()
     assert L.device_error_flag() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["fine", "coarse"])
+def test_canvas_scatter_kernel_vs_reference_fixture(canvas_golden, name):
+    """The device-side assembly against the output of the reference's own render(): bit for bit."""
+    from moco_flow_b200 import camera
+    g = canvas_golden
+    dev = torch.device("cuda:0")
+    pix = torch.from_numpy(np.where(g[f"{name}_rays_msk"])[0]).to(dev)
+    bg, rgb, depth, opacity = (torch.from_numpy(g[f"{name}_{k}"]).to(dev) for k in ("background", "rgb", "depth", "opacity"))
+    img, dep = camera.scatter_canvas(bg, pix, rgb, depth, opacity)
+    assert np.array_equal(img.cpu().numpy(), g[f"{name}_img"])
+    assert np.array_equal(dep.cpu().numpy(), g[f"{name}_depth_img"])
 
 
 @pytest.mark.gpu
